@@ -1,0 +1,135 @@
+/*
+ * irb.h -- C ABI of the B200-native render-layer + bilateral-solver library
+ * (libirb_b200.so, built from inverserenderingofindoorscene_b200/csrc/).
+ *
+ * This is the drop-in boundary for the hot path of lzqsd/InverseRenderingOfIndoorScene
+ * (SURVEY.md 8b).  The reference is pure Python: the "FFI" a maintainer binds is ctypes
+ * (see INTEGRATION.md).  Every entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - all tensor pointers are DEVICE pointers to contiguous fp32 (unless stated), NCHW-style
+ *     layouts exactly as the reference's PyTorch tensors; the caller owns every buffer
+ *     (outputs and workspaces included) -- the library never allocates device memory;
+ *   - `stream` is a cudaStream_t passed as void*; kernels are launched asynchronously on it,
+ *     no entry point synchronises the device except where stated;
+ *   - the device is the caller's current device (cudaSetDevice done by the caller);
+ *   - return 0 on success, negative for argument errors (IRB_E_*), positive = cudaError_t;
+ *     a thread-local message is available from irb_last_error();
+ *   - gradient outputs may be NULL = "not needed"; they are OVERWRITTEN, not accumulated;
+ *   - B batch, K SG lobes, R x C render (env) grid, envH x envW hemisphere table
+ *     (D = envH*envW <= IRB_MAX_DIRS), direction index d = i*envW + j.
+ */
+#ifndef IRB_H_
+#define IRB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IRB_ABI_VERSION 1
+#define IRB_MAX_DIRS 128
+#define IRB_MAX_LOBES 48
+
+#define IRB_E_ARG (-1)     /* bad shape / null pointer */
+#define IRB_E_UNSUPPORTED (-2)
+#define IRB_E_WORKSPACE (-3)
+
+int irb_abi_version(void);
+const char* irb_last_error(void);
+
+/* ---------------------------------------------------------------------------------------
+ * SG lobes -> hemisphere env-map.  Replaces models.output2env.fromSGtoIm (models.py:371-389)
+ * and, with warp=1, models.output2env.output2env (models.py:391-404):
+ *   lam = tan(pi/2*0.999*lamb), W = tan(pi/2*0.999*weight)   (warp=1; identity if warp=0)
+ *   env[b,c,r,x,d] = sum_k W[b,3k+c,r,x] * exp(lam[b,k,r,x]*(axis[b,k,:,r,x].ls[d] - 1))
+ * axis [B,K,3,R,C], lamb [B,K,R,C], weight [B,3K,R,C], env [B,3,R,C,envH,envW].
+ * lamb_w / weight_w (optional, may be NULL): the warped lam / W ([B,K,R,C] / [B,3K,R,C]) that
+ * output2env returns as its 3rd/4th results.
+ * ------------------------------------------------------------------------------------- */
+int irb_sg_to_env_fwd(const float* axis, const float* lamb, const float* weight, float* env,
+                      float* lamb_w, float* weight_w,
+                      int B, int K, int R, int C, int envH, int envW, int warp, void* stream);
+
+/* Backward of the above (autograd of models.py:371-404).  g_env [B,3,R,C,envH,envW];
+ * g_axis / g_lamb / g_weight shaped like the inputs; gradients are w.r.t. the RAW inputs
+ * when warp=1 (chain through tan), w.r.t. lam / W when warp=0. */
+int irb_sg_to_env_bwd(const float* axis, const float* lamb, const float* weight, const float* g_env,
+                      float* g_axis, float* g_lamb, float* g_weight,
+                      int B, int K, int R, int C, int envH, int envW, int warp, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Microfacet shading of a materialised env-map.  Replaces the body of
+ * models.renderingLayer.forwardEnv after pooling (models.py:466-520).
+ * albedo/normal [B,3,R,C], rough [B,1,R,C] are the POOLED maps (see irb_avgpool_*);
+ * env [B,3,R,C,envH,envW]; view [3,R,C] = renderingLayer.v (models.py:428-432);
+ * out_diff / out_spec [B,3,R,C].
+ * ------------------------------------------------------------------------------------- */
+int irb_render_env_fwd(const float* albedo, const float* normal, const float* rough, const float* env,
+                       const float* view, float* out_diff, float* out_spec,
+                       int B, int R, int C, int envH, int envW, float F0, void* stream);
+
+int irb_render_env_bwd(const float* albedo, const float* normal, const float* rough, const float* env,
+                       const float* view, const float* g_diff, const float* g_spec,
+                       float* g_albedo, float* g_normal, float* g_rough, float* g_env,
+                       int B, int R, int C, int envH, int envW, float F0, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * FUSED SG-lit render (the north-star kernel): output2env.output2env followed by
+ * renderingLayer.forwardEnv (wrapperBRDFLight.py:177,194) without materialising the env-map.
+ * Inputs as above; lamb / weight are the RAW decoder outputs when warp=1.
+ * ------------------------------------------------------------------------------------- */
+int irb_render_sg_fwd(const float* albedo, const float* normal, const float* rough,
+                      const float* axis, const float* lamb, const float* weight, const float* view,
+                      float* out_diff, float* out_spec,
+                      int B, int K, int R, int C, int envH, int envW, float F0, int warp, void* stream);
+
+int irb_render_sg_bwd(const float* albedo, const float* normal, const float* rough,
+                      const float* axis, const float* lamb, const float* weight, const float* view,
+                      const float* g_diff, const float* g_spec,
+                      float* g_albedo, float* g_normal, float* g_rough,
+                      float* g_axis, float* g_lamb, float* g_weight,
+                      int B, int K, int R, int C, int envH, int envW, float F0, int warp, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * F.adaptive_avg_pool2d as used at models.py:465-469 (window [floor(i*H/R), ceil((i+1)*H/R))).
+ * in [N,H,W] -> out [N,R,C] (N = B*channels); bwd spreads g_out uniformly over each window.
+ * ------------------------------------------------------------------------------------- */
+int irb_avgpool_fwd(const float* in, float* out, int N, int H, int W, int R, int C, void* stream);
+int irb_avgpool_bwd(const float* g_out, float* g_in, int N, int H, int W, int R, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Bilateral-grid solver.  Replaces BilateralGrid.BilateralGrid / bistochastize /
+ * BilateralSolver.solve / solveGrad (BilateralGrid.py:44-207) and the per-image bridge
+ * BilateralLayer.BilateralFunction.forward/backward (BilateralLayer.py:24-124).
+ *
+ * irb_bg_workspace_bytes: size of the opaque grid workspace for B images of H x W.
+ * irb_bg_build: guide [B,3,H,W] in [0,1] (multiplied by 255.0f in fp32 as BilateralLayer.py:52
+ *   does), builds per image the 5-D XYLUV grid (fp64 coordinates, BilateralGrid.py:44-59),
+ *   vertex ids = rank of the hash among sorted unique hashes (BilateralGrid.py:61-65),
+ *   the +-1 neighbour table (:72-84) and the bistochastisation vectors (:109-120).
+ *   nverts_out: HOST int[B], written after an internal stream synchronise (the only sync).
+ * irb_bg_vertex_index: copies the per-pixel vertex ids (int32 [B,H*W]) for inspection.
+ * irb_bg_solve_fwd: pred [B,ch,H,W], conf [B,1,H,W] -> out [B,ch,H,W];
+ *   yhat (fp64, [B, ch, H*W] capacity) receives the bilateral-space solution saved for backward.
+ * irb_bg_solve_bwd: adjoint solve (BilateralGrid.py:152-184) -> g_pred [B,ch,H,W], g_conf [B,1,H,W].
+ * cg_maxiter is an explicit integer (the reference reads it from the wrong slot,
+ * BilateralLayer.py:44,79).
+ * ------------------------------------------------------------------------------------- */
+size_t irb_bg_workspace_bytes(int B, int H, int W, int ch);
+int irb_bg_build(const float* guide, int B, int H, int W, double sigma_luma, double sigma_chroma,
+                 double sigma_spatial, void* ws, size_t ws_bytes, int* nverts_out, void* stream);
+int irb_bg_vertex_index(const void* ws, int32_t* idx_out, int B, int H, int W, void* stream);
+int irb_bg_solve_fwd(void* ws, const float* pred, const float* conf, int B, int ch, int H, int W,
+                     double lam, double A_diag_min, double cg_tol, int cg_maxiter,
+                     float* out, double* yhat, void* stream);
+int irb_bg_solve_bwd(void* ws, const float* pred, const float* conf, const float* g_out, const double* yhat,
+                     int B, int ch, int H, int W, double lam, double A_diag_min, double cg_tol, int cg_maxiter,
+                     float* g_pred, float* g_conf, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IRB_H_ */

@@ -1,0 +1,226 @@
+// irb_driver.cuh -- per-pixel drivers of the fused SG render: load one pixel's planes, run the
+// register-resident sweeps of irb_pixel.cuh, store results.  One CUDA thread runs one driver
+// call (thread-per-pixel: the lobe parameters, their gradient accumulators and the BRDF state
+// all live in registers; channel-planar tensors make every load/store coalesced across the
+// warp).  The same code is instantiated on the host by tests/hostcheck (T = float / double).
+#pragma once
+#include "irb_pixel.cuh"
+
+namespace irb {
+
+struct RenderSgArgs {
+    // inputs (models.py:461 forwardEnv + models.py:391 output2env)
+    const float* albedo;  // [B,3,R,C] pooled
+    const float* normal;  // [B,3,R,C] pooled, un-normalised
+    const float* rough;   // [B,1,R,C] pooled
+    const float* axis;    // [B,K,3,R,C]
+    const float* lamb;    // [B,K,R,C]
+    const float* weight;  // [B,3K,R,C]  channel = 3k+c
+    const float* view;    // [3,R,C]
+    // forward outputs
+    float* out_diff;  // [B,3,R,C]
+    float* out_spec;
+    // backward
+    const float* g_diff;
+    const float* g_spec;
+    float* g_albedo;
+    float* g_normal;
+    float* g_rough;
+    float* g_axis;
+    float* g_lamb;
+    float* g_weight;
+    int B, K, R, C;
+    float F0;
+    int warp;
+};
+
+template <typename T, int KC>
+IRB_HD void load_lobes(Lobes<T, KC>& L, const RenderSgArgs& a, size_t b, size_t pix, size_t plane, int k0) {
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        const int kk = k0 + k;
+        if (kk < a.K) {
+            const size_t oa = ((b * a.K + kk) * 3) * plane + pix;
+            L.ax[k] = (T)a.axis[oa];
+            L.ay[k] = (T)a.axis[oa + plane];
+            L.az[k] = (T)a.axis[oa + 2 * plane];
+            T lam = (T)a.lamb[(b * a.K + kk) * plane + pix];
+            if (a.warp) lam = sg_warp<T>(lam);
+            L.lam[k] = lam * Consts<T>::LOG2E;
+        } else {  // padding lobe: contributes exactly zero (its weight is taken as 0)
+            L.ax[k] = L.ay[k] = L.az[k] = T(0);
+            L.lam[k] = T(0);
+        }
+    }
+}
+
+template <typename T> IRB_HD T load_weight(const RenderSgArgs& a, size_t b, size_t pix, size_t plane, int kk, int c) {
+    T w = (T)a.weight[(b * (3 * a.K) + 3 * kk + c) * plane + pix];
+    if (a.warp) w = sg_warp<T>(w);
+    return w;
+}
+
+template <typename T>
+IRB_HD void load_pixel(Pixel<T>& px, V3<T>& nt, T (&A)[3], const RenderSgArgs& a, size_t b, size_t pix, size_t plane) {
+    const size_t o3 = (b * 3) * plane + pix;
+    nt = V3<T>{(T)a.normal[o3], (T)a.normal[o3 + plane], (T)a.normal[o3 + 2 * plane]};
+    A[0] = (T)a.albedo[o3];
+    A[1] = (T)a.albedo[o3 + plane];
+    A[2] = (T)a.albedo[o3 + 2 * plane];
+    const V3<T> v{(T)a.view[pix], (T)a.view[plane + pix], (T)a.view[2 * plane + pix]};
+    pixel_setup(px, nt, (T)a.rough[b * plane + pix], v, (T)a.F0);
+}
+
+// ---- forward: out_diff, out_spec --------------------------------------------------------
+template <typename T, int KC>
+IRB_HD void drv_render_sg_fwd(const RenderSgArgs& a, const EnvTab& tab, size_t b, size_t pix) {
+    const size_t plane = (size_t)a.R * a.C;
+    Pixel<T> px;
+    V3<T> nt;
+    T A[3];
+    load_pixel(px, nt, A, a, b, pix, plane);
+    T Dc[3] = {0, 0, 0}, Sc[3] = {0, 0, 0};
+    for (int k0 = 0; k0 < a.K; k0 += KC) {
+        Lobes<T, KC> L;
+        load_lobes(L, a, b, pix, plane, k0);
+        T U[KC], V[KC];
+        sweep_fwd<T, KC>(px, L, tab, U, V);
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            if (k0 + k < a.K) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const T w = load_weight<T>(a, b, pix, plane, k0 + k, c);
+                    Dc[c] += w * U[k];
+                    Sc[c] += w * V[k];
+                }
+            }
+        }
+    }
+    const size_t o3 = (b * 3) * plane + pix;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        a.out_diff[o3 + c * plane] = (float)(A[c] * Consts<T>::INV_PI * Dc[c]);
+        a.out_spec[o3 + c * plane] = (float)Sc[c];
+    }
+}
+
+// ---- backward -----------------------------------------------------------------------------
+// KP: chunk width of the BRDF-side sweep (must cover all K lobes); KL: chunk width of the
+// SG-side sweeps.  When KP == KL and K <= KP a single sweep does both.
+template <typename T, int KC>
+IRB_HD void load_PQ(T (&P)[KC], T (&Q)[KC], const RenderSgArgs& a, size_t b, size_t pix, size_t plane, int k0,
+                    const T (&gDa)[3], const T (&gS)[3]) {
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        P[k] = Q[k] = T(0);
+        if (k0 + k < a.K) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const T w = load_weight<T>(a, b, pix, plane, k0 + k, c);
+                P[k] += gDa[c] * w;
+                Q[k] += gS[c] * w;
+            }
+        }
+    }
+}
+
+template <typename T, int KC>
+IRB_HD void store_lobe_grads(const LobeGrads<T, KC>& lg, const Lobes<T, KC>& L, const RenderSgArgs& a, size_t b, size_t pix,
+                             size_t plane, int k0, const T (&gDa)[3], const T (&gS)[3], T (&gAlb)[3]) {
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        const int kk = k0 + k;
+        if (kk < a.K) {
+            const T lam = L.lam[k] * Consts<T>::LN2;  // undo the log2e fold
+            if (a.g_axis) {
+                const size_t oa = ((b * a.K + kk) * 3) * plane + pix;
+                a.g_axis[oa] = (float)(lam * lg.mx[k]);
+                a.g_axis[oa + plane] = (float)(lam * lg.my[k]);
+                a.g_axis[oa + 2 * plane] = (float)(lam * lg.mz[k]);
+            }
+            if (a.g_lamb) {
+                T g = lg.gl[k];
+                if (a.warp) g *= sg_warp_grad<T>(lam);
+                a.g_lamb[(b * a.K + kk) * plane + pix] = (float)g;
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const T w = load_weight<T>(a, b, pix, plane, kk, c);
+                gAlb[c] += w * lg.U[k];
+                if (a.g_weight) {
+                    T g = gDa[c] * lg.U[k] + gS[c] * lg.V[k];
+                    if (a.warp) g *= sg_warp_grad<T>(w);
+                    a.g_weight[(b * (3 * a.K) + 3 * kk + c) * plane + pix] = (float)g;
+                }
+            }
+        }
+    }
+}
+
+template <typename T, int KP, int KL, bool PIX, bool LOBE>
+IRB_HD void drv_render_sg_bwd(const RenderSgArgs& a, const EnvTab& tab, size_t b, size_t pix) {
+    const size_t plane = (size_t)a.R * a.C;
+    Pixel<T> px;
+    V3<T> nt;
+    T A[3];
+    load_pixel(px, nt, A, a, b, pix, plane);
+    const size_t o3 = (b * 3) * plane + pix;
+    T gD[3], gS[3], gDa[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        gD[c] = (T)a.g_diff[o3 + c * plane];
+        gS[c] = (T)a.g_spec[o3 + c * plane];
+        gDa[c] = gD[c] * A[c] * Consts<T>::INV_PI;
+    }
+    PixelGrad<T> pg;
+    pixel_grad_zero(pg);
+    T gAlb[3] = {0, 0, 0};
+    if (KP == KL) {
+        // single sweep: all lobes in one chunk
+        Lobes<T, KP> L;
+        load_lobes(L, a, b, pix, plane, 0);
+        T P[KP], Q[KP];
+        load_PQ<T, KP>(P, Q, a, b, pix, plane, 0, gDa, gS);
+        LobeGrads<T, KP> lg;
+        sweep_bwd<T, KP, PIX, LOBE>(px, L, P, Q, tab, pg, lg);
+        if (LOBE) store_lobe_grads<T, KP>(lg, L, a, b, pix, plane, 0, gDa, gS, gAlb);
+    } else {
+        if (PIX) {
+            Lobes<T, KP> L;
+            load_lobes(L, a, b, pix, plane, 0);
+            T P[KP], Q[KP];
+            load_PQ<T, KP>(P, Q, a, b, pix, plane, 0, gDa, gS);
+            LobeGrads<T, KP> lg;  // unused
+            sweep_bwd<T, KP, true, false>(px, L, P, Q, tab, pg, lg);
+        }
+        if (LOBE) {
+            for (int k0 = 0; k0 < a.K; k0 += KL) {
+                Lobes<T, KL> L;
+                load_lobes(L, a, b, pix, plane, k0);
+                T P[KL], Q[KL];
+                load_PQ<T, KL>(P, Q, a, b, pix, plane, k0, gDa, gS);
+                LobeGrads<T, KL> lg;
+                sweep_bwd<T, KL, false, true>(px, L, P, Q, tab, pg, lg);
+                store_lobe_grads<T, KL>(lg, L, a, b, pix, plane, k0, gDa, gS, gAlb);
+            }
+        }
+    }
+    if (PIX) {
+        V3<T> g_nt;
+        T g_rough;
+        pixel_bwd_finish(pg, px, nt, g_nt, g_rough);
+        if (a.g_normal) {
+            a.g_normal[o3] = (float)g_nt.x;
+            a.g_normal[o3 + plane] = (float)g_nt.y;
+            a.g_normal[o3 + 2 * plane] = (float)g_nt.z;
+        }
+        if (a.g_rough) a.g_rough[b * plane + pix] = (float)g_rough;
+    }
+    if (LOBE && a.g_albedo) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a.g_albedo[o3 + c * plane] = (float)(gD[c] * Consts<T>::INV_PI * gAlb[c]);
+    }
+}
+
+}  // namespace irb

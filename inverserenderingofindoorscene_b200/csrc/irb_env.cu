@@ -1,0 +1,117 @@
+// irb_env.cu -- UNFUSED boundary kernels over a materialised env-map [B,3,R,C,envH,envW]:
+//   sg_to_env fwd/bwd   (models.output2env.fromSGtoIm / output2env, models.py:371-404)
+//   render_env fwd/bwd  (models.renderingLayer.forwardEnv after pooling, models.py:466-520)
+// Thread-per-pixel like the fused kernel; the env-map is read/written as 16-byte vectors along
+// the direction axis (a pixel's 128 directions of one channel are one 512-byte run, so every
+// 32-byte sector fetched is fully used by the thread that fetched it).  These are the exact
+// drop-ins for callers that hand forwardEnv an arbitrary env tensor; the fused kernel in
+// irb_render_sg.cu is the fast path when the env-map comes from SG lobes.
+#include "irb_common.cuh"
+#include "irb_driver_env.cuh"
+
+namespace irb {
+
+constexpr int kThreadsEnv = 128;
+
+template <int KC>
+__global__ void __launch_bounds__(kThreadsEnv) sg_to_env_fwd_kernel(const SgEnvArgs s, const __grid_constant__ EnvTab tab) {
+    const size_t pix = (size_t)blockIdx.x * kThreadsEnv + threadIdx.x;
+    if (pix >= (size_t)s.R * s.C) return;
+    drv_sg_to_env_fwd<float, KC>(s, tab, blockIdx.y, pix);
+}
+template <int KC>
+__global__ void __launch_bounds__(kThreadsEnv) sg_to_env_bwd_kernel(const SgEnvArgs s, const __grid_constant__ EnvTab tab) {
+    const size_t pix = (size_t)blockIdx.x * kThreadsEnv + threadIdx.x;
+    if (pix >= (size_t)s.R * s.C) return;
+    drv_sg_to_env_bwd<float, KC>(s, tab, blockIdx.y, pix);
+}
+__global__ void __launch_bounds__(kThreadsEnv) render_env_fwd_kernel(const RenderEnvArgs s, const __grid_constant__ EnvTab tab) {
+    const size_t pix = (size_t)blockIdx.x * kThreadsEnv + threadIdx.x;
+    if (pix >= (size_t)s.R * s.C) return;
+    drv_render_env_fwd<float>(s, tab, blockIdx.y, pix);
+}
+__global__ void __launch_bounds__(kThreadsEnv) render_env_bwd_kernel(const RenderEnvArgs s, const __grid_constant__ EnvTab tab) {
+    const size_t pix = (size_t)blockIdx.x * kThreadsEnv + threadIdx.x;
+    if (pix >= (size_t)s.R * s.C) return;
+    drv_render_env_bwd<float>(s, tab, blockIdx.y, pix);
+}
+
+static int mk_tab(EnvTab& tab, int envH, int envW, int B, const char* who) {
+    if (!make_env_tab(tab, envH, envW)) {
+        set_error("%s: env table %dx%d unsupported (need envH*envW <= %d, multiple of 4)", who, envH, envW, IRB_MAX_DIRS);
+        return IRB_E_UNSUPPORTED;
+    }
+    if (B > 65535) {
+        set_error("%s: B=%d exceeds grid.y", who, B);
+        return IRB_E_UNSUPPORTED;
+    }
+    return 0;
+}
+
+}  // namespace irb
+
+using namespace irb;
+
+extern "C" int irb_sg_to_env_fwd(const float* axis, const float* lamb, const float* weight, float* env, float* lamb_w,
+                                 float* weight_w, int B, int K, int R, int C, int envH, int envW, int warp, void* stream) {
+    IRB_REQUIRE(B > 0 && K > 0 && R > 0 && C > 0, "sg_to_env_fwd: non-positive shape");
+    IRB_REQUIRE(axis && lamb && weight && env, "sg_to_env_fwd: null pointer");
+    EnvTab tab;
+    if (int rc = mk_tab(tab, envH, envW, B, "sg_to_env_fwd")) return rc;
+    SgEnvArgs s{};
+    s.axis = axis; s.lamb = lamb; s.weight = weight; s.env = env; s.lamb_w = lamb_w; s.weight_w = weight_w;
+    s.B = B; s.K = K; s.R = R; s.C = C; s.warp = warp;
+    const dim3 grid((unsigned)(((size_t)R * C + kThreadsEnv - 1) / kThreadsEnv), (unsigned)B);
+    sg_to_env_fwd_kernel<12><<<grid, kThreadsEnv, 0, (cudaStream_t)stream>>>(s, tab);
+    return check_launch("sg_to_env_fwd");
+}
+
+extern "C" int irb_sg_to_env_bwd(const float* axis, const float* lamb, const float* weight, const float* g_env,
+                                 float* g_axis, float* g_lamb, float* g_weight, int B, int K, int R, int C, int envH,
+                                 int envW, int warp, void* stream) {
+    IRB_REQUIRE(B > 0 && K > 0 && R > 0 && C > 0, "sg_to_env_bwd: non-positive shape");
+    IRB_REQUIRE(axis && lamb && weight && g_env, "sg_to_env_bwd: null pointer");
+    EnvTab tab;
+    if (int rc = mk_tab(tab, envH, envW, B, "sg_to_env_bwd")) return rc;
+    SgEnvArgs s{};
+    s.axis = axis; s.lamb = lamb; s.weight = weight; s.g_env = g_env;
+    s.g_axis = g_axis; s.g_lamb = g_lamb; s.g_weight = g_weight;
+    s.B = B; s.K = K; s.R = R; s.C = C; s.warp = warp;
+    const dim3 grid((unsigned)(((size_t)R * C + kThreadsEnv - 1) / kThreadsEnv), (unsigned)B);
+    sg_to_env_bwd_kernel<12><<<grid, kThreadsEnv, 0, (cudaStream_t)stream>>>(s, tab);
+    return check_launch("sg_to_env_bwd");
+}
+
+extern "C" int irb_render_env_fwd(const float* albedo, const float* normal, const float* rough, const float* env,
+                                  const float* view, float* out_diff, float* out_spec, int B, int R, int C, int envH,
+                                  int envW, float F0, void* stream) {
+    IRB_REQUIRE(B > 0 && R > 0 && C > 0, "render_env_fwd: non-positive shape");
+    IRB_REQUIRE(albedo && normal && rough && env && view && out_diff && out_spec, "render_env_fwd: null pointer");
+    EnvTab tab;
+    if (int rc = mk_tab(tab, envH, envW, B, "render_env_fwd")) return rc;
+    RenderEnvArgs s{};
+    s.albedo = albedo; s.normal = normal; s.rough = rough; s.env = env; s.view = view;
+    s.out_diff = out_diff; s.out_spec = out_spec;
+    s.B = B; s.R = R; s.C = C; s.F0 = F0;
+    const dim3 grid((unsigned)(((size_t)R * C + kThreadsEnv - 1) / kThreadsEnv), (unsigned)B);
+    render_env_fwd_kernel<<<grid, kThreadsEnv, 0, (cudaStream_t)stream>>>(s, tab);
+    return check_launch("render_env_fwd");
+}
+
+extern "C" int irb_render_env_bwd(const float* albedo, const float* normal, const float* rough, const float* env,
+                                  const float* view, const float* g_diff, const float* g_spec, float* g_albedo,
+                                  float* g_normal, float* g_rough, float* g_env, int B, int R, int C, int envH, int envW,
+                                  float F0, void* stream) {
+    IRB_REQUIRE(B > 0 && R > 0 && C > 0, "render_env_bwd: non-positive shape");
+    IRB_REQUIRE(albedo && normal && rough && env && view && g_diff && g_spec, "render_env_bwd: null pointer");
+    EnvTab tab;
+    if (int rc = mk_tab(tab, envH, envW, B, "render_env_bwd")) return rc;
+    RenderEnvArgs s{};
+    s.albedo = albedo; s.normal = normal; s.rough = rough; s.env = env; s.view = view;
+    s.g_diff = g_diff; s.g_spec = g_spec;
+    s.g_albedo = g_albedo; s.g_normal = g_normal; s.g_rough = g_rough; s.g_env = g_env;
+    s.B = B; s.R = R; s.C = C; s.F0 = F0;
+    const dim3 grid((unsigned)(((size_t)R * C + kThreadsEnv - 1) / kThreadsEnv), (unsigned)B);
+    render_env_bwd_kernel<<<grid, kThreadsEnv, 0, (cudaStream_t)stream>>>(s, tab);
+    return check_launch("render_env_bwd");
+}

@@ -1,0 +1,320 @@
+// irb_math.cuh -- per-pixel / per-direction shading math of the render layer, shared by the
+// unfused (render_env) and fused (render_sg) kernels.  Templated on the scalar type so that
+// tests/hostcheck can instantiate the SAME code on the host in float and double and compare
+// it with the oracle without a GPU (test infrastructure; the product only uses the float
+// device instantiation).
+//
+// Follows /root/reference/models.py:461-522 (renderingLayer.forwardEnv); the hand-derived
+// backward follows autograd of those lines (clamp pass-through inclusive, F.normalize eps
+// semantics), SURVEY.md Appendix A.
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define IRB_HD __host__ __device__ __forceinline__
+#else
+#define IRB_HD inline
+#endif
+
+namespace irb {
+
+template <typename T> struct Consts;
+template <> struct Consts<float> {
+    static constexpr float PI = 3.14159265358979323846f;
+    static constexpr float INV_PI = 0.31830988618379067154f;
+    static constexpr float FOUR_PI = 12.566370614359172f;
+    static constexpr float LN2 = 0.69314718055994530942f;
+    static constexpr float LOG2E = 1.44269504088896340736f;
+};
+template <> struct Consts<double> {
+    static constexpr double PI = 3.14159265358979323846;
+    static constexpr double INV_PI = 0.31830988618379067154;
+    static constexpr double FOUR_PI = 12.566370614359172;
+    static constexpr double LN2 = 0.69314718055994530942;
+    static constexpr double LOG2E = 1.44269504088896340736;
+};
+
+// ---- scalar primitives (device fp32 uses the SFU approximations where accuracy allows) ----
+IRB_HD float x_exp2(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return exp2f(x);
+#endif
+}
+IRB_HD double x_exp2(double x) { return exp2(x); }
+IRB_HD float x_rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+IRB_HD double x_rsqrt(double x) { return 1.0 / sqrt(x); }
+IRB_HD float x_sqrt(float x) { return sqrtf(x); }
+IRB_HD double x_sqrt(double x) { return sqrt(x); }
+IRB_HD float x_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    return __frcp_rn(x);
+#else
+    return 1.0f / x;
+#endif
+}
+IRB_HD double x_rcp(double x) { return 1.0 / x; }
+IRB_HD float x_mul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    volatile float r = a * b;
+    return r;
+#endif
+}
+IRB_HD float x_add(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    volatile float r = a + b;
+    return r;
+#endif
+}
+IRB_HD double x_mul(double a, double b) { return a * b; }
+IRB_HD double x_add(double a, double b) { return a + b; }
+IRB_HD float x_fma(float a, float b, float c) { return fmaf(a, b, c); }
+IRB_HD double x_fma(double a, double b, double c) { return fma(a, b, c); }
+template <typename T> IRB_HD T x_min(T a, T b) { return a < b ? a : b; }
+template <typename T> IRB_HD T x_max(T a, T b) { return a > b ? a : b; }
+template <typename T> IRB_HD T x_clamp(T x, T lo, T hi) { return x_min(x_max(x, lo), hi); }
+
+template <typename T> struct V3 {
+    T x, y, z;
+};
+template <typename T> IRB_HD T dot(const V3<T>& a, const V3<T>& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <typename T> IRB_HD V3<T> cross(const V3<T>& a, const V3<T>& b) {
+    return V3<T>{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+template <typename T> IRB_HD V3<T> axpy(T a, const V3<T>& x, const V3<T>& y) {
+    return V3<T>{a * x.x + y.x, a * x.y + y.y, a * x.z + y.z};
+}
+template <typename T> IRB_HD V3<T> scale(T a, const V3<T>& x) { return V3<T>{a * x.x, a * x.y, a * x.z}; }
+
+// ---- tan warp of SG sharpness / intensity (models.py:396-400) ---------------------------
+// y = tan(pi/2 * 0.999 * x).  Near x -> 1 the derivative reaches 4e5, so one ulp of the
+// fp32 argument is ~4e-5 relative in y.  The complement t = 1 - 0.999 x is formed with 0.999
+// split in two floats and y = cot(pi/2 * t), which keeps the result within ~3e-7 of the
+// exact value for fp32 inputs (the fp64 oracle's value).
+template <typename T> IRB_HD T sg_warp(T x);
+template <> IRB_HD double sg_warp<double>(double x) { return tan(Consts<double>::PI / 2 * (0.999 * x)); }
+template <> IRB_HD float sg_warp<float>(float x) {
+    const float c_hi = 0.999f;                                   // fl(0.999)
+    const float c_lo = (float)(0.999 - (double)0.999f);          // residual
+    float t = fmaf(-c_hi, x, 1.0f);
+    t = fmaf(-c_lo, x, t);                                       // t = 1 - 0.999 x  (x in [0,1])
+    const float y = 1.57079632679489661923f * t;                 // in (0.0015, pi/2]
+    float s, c;
+#if defined(__CUDA_ARCH__)
+    sincosf(y, &s, &c);
+#else
+    s = sinf(y);
+    c = cosf(y);
+#endif
+    return c / s;
+}
+// d tan(c x)/dx = c (1 + tan^2)
+template <typename T> IRB_HD T sg_warp_grad(T y) {
+    return (T)(Consts<double>::PI / 2 * 0.999) * (T(1) + y * y);
+}
+
+// ---- per-pixel state ----------------------------------------------------------------------
+template <typename T> struct Pixel {
+    V3<T> n, camx, camy, v;   // shading normal, local frame, view vector
+    T s, inv;                 // |n~|^2, 1/sqrt(clamp(s))
+    T nn_dev;                 // |n|^2 - 1 in exact arithmetic (0 unless the s clamp is active)
+    T un, pn, qn;             // up.n, clamped |p|, clamped |q|
+    bool p_ok, q_ok;          // norms above F.normalize eps
+    T rho, k, alpha2, ndv_raw, ndv, n1, F0;
+};
+
+// models.py:466-468, 477-480, 493-500
+template <typename T>
+IRB_HD void pixel_setup(Pixel<T>& px, const V3<T>& nt, T rough, const V3<T>& v, T F0) {
+    px.v = v;
+    px.F0 = F0;
+    // (x^2 + y^2) + z^2 with separate roundings (no FMA contraction): the same value ATen's
+    // torch.sum(n*n, dim=1) produces, so the clamp(s, 1e-6, 1) regime (models.py:467-468) is
+    // decided exactly as the reference's fp32 run decides it.
+    px.s = x_add(x_add(x_mul(nt.x, nt.x), x_mul(nt.y, nt.y)), x_mul(nt.z, nt.z));
+    const T sc = x_clamp(px.s, (T)1e-6, (T)1);
+    px.inv = x_rsqrt(sc);
+    px.n = scale(px.inv, nt);
+    if (px.s > T(1)) {
+        // upper clamp: n = n~, |n|^2 - 1 = s - 1 with s summed without cancellation error
+        const T xx = nt.x * nt.x, yy = nt.y * nt.y, zz = nt.z * nt.z;
+        px.nn_dev = ((xx - T(1)) + yy + zz) + (x_fma(nt.x, nt.x, -xx) + x_fma(nt.y, nt.y, -yy) + x_fma(nt.z, nt.z, -zz));
+    } else if (px.s < (T)1e-6) {
+        px.nn_dev = px.s * (T)1e6 - T(1);
+    } else {
+        px.nn_dev = T(0);
+    }
+    px.un = px.n.y;
+    const V3<T> p{-px.un * px.n.x, T(1) - px.un * px.n.y, -px.un * px.n.z};
+    const T pl = x_sqrt(dot(p, p));
+    px.p_ok = pl >= (T)1e-12;
+    px.pn = x_max(pl, (T)1e-12);
+    px.camy = scale(T(1) / px.pn, p);
+    const V3<T> q = cross(px.camy, px.n);
+    const T ql = x_sqrt(dot(q, q));
+    px.q_ok = ql >= (T)1e-12;
+    px.qn = x_max(ql, (T)1e-12);
+    px.camx = scale(T(-1) / px.qn, q);
+    px.rho = (rough + T(1)) * T(0.5);
+    px.k = (px.rho + T(1)) * (px.rho + T(1)) * T(0.125);
+    const T a = px.rho * px.rho;
+    px.alpha2 = a * a;
+    px.ndv_raw = dot(px.n, v);
+    px.ndv = x_clamp(px.ndv_raw, T(0), T(1));
+    px.n1 = px.ndv * (T(1) - px.k) + px.k;
+}
+
+// per-direction forward quantities (kept for the backward of the same direction)
+template <typename T> struct Dir {
+    V3<T> l, h;
+    T mm, rinv, vdh, p2, F, ndh_raw, ndh, ndl_raw, ndl, n0, n2, nom_raw, nom, spec;
+};
+
+// models.py:482-509.  (wx,wy,wz) = ls[d]
+template <typename T> IRB_HD void dir_fwd(Dir<T>& dr, const Pixel<T>& px, T wx, T wy, T wz) {
+    dr.l = V3<T>{wx * px.camx.x + wy * px.camy.x + wz * px.n.x, wx * px.camx.y + wy * px.camy.y + wz * px.n.y,
+                 wx * px.camx.z + wy * px.camy.z + wz * px.n.z};
+    const V3<T> m{(px.v.x + dr.l.x) * T(0.5), (px.v.y + dr.l.y) * T(0.5), (px.v.z + dr.l.z) * T(0.5)};
+    dr.mm = dot(m, m);
+    dr.rinv = x_rsqrt(x_max(dr.mm, (T)1e-6));
+    dr.h = scale(dr.rinv, m);
+    dr.vdh = dot(px.v, dr.h);
+    dr.p2 = x_exp2((T(-5.55472) * dr.vdh - T(6.98316)) * dr.vdh);
+    dr.F = px.F0 + (T(1) - px.F0) * dr.p2;
+    dr.ndh_raw = dot(px.n, dr.h);
+    dr.ndh = x_clamp(dr.ndh_raw, T(0), T(1));
+    dr.ndl_raw = dot(px.n, dr.l);
+    dr.ndl = x_clamp(dr.ndl_raw, T(0), T(1));
+    // n0 = ndh^2 (alpha2-1) + 1 (models.py:504) cancels catastrophically for glossy pixels near the
+    // highlight (n0 -> alpha2 ~ 1e-3).  Evaluate it as (1-ndh)(1+ndh) + alpha2 ndh^2 with
+    // 1-ndh = |n-h|^2/2 + (1 - (|n|^2+|h|^2)/2), which has no cancellation; px.nn_dev and the mm
+    // clamp carry the (rare) non-unit cases exactly.
+    if (dr.ndh_raw <= T(0)) {
+        dr.n0 = T(1);
+    } else if (dr.ndh_raw >= T(1)) {
+        dr.n0 = px.alpha2;
+    } else {
+        const T dx = px.n.x - dr.h.x, dy = px.n.y - dr.h.y, dz = px.n.z - dr.h.z;
+        const T hh_dev = (dr.mm >= (T)1e-6) ? T(0) : dr.mm * (T)1e6 - T(1);
+        const T one_m = T(0.5) * (dx * dx + dy * dy + dz * dz) - T(0.5) * (px.nn_dev + hh_dev);
+        dr.n0 = one_m * (T(1) + dr.ndh) + px.alpha2 * dr.ndh * dr.ndh;
+    }
+    dr.n2 = dr.ndl * (T(1) - px.k) + px.k;
+    dr.nom_raw = Consts<T>::FOUR_PI * dr.n0 * dr.n0 * px.n1 * dr.n2;
+    dr.nom = x_clamp(dr.nom_raw, (T)1e-6, Consts<T>::FOUR_PI);
+    dr.spec = px.alpha2 * dr.F * x_rcp(dr.nom);
+}
+
+// accumulators of the per-pixel backward
+template <typename T> struct PixelGrad {
+    V3<T> g_cx, g_cy, g_n;
+    T G_n1, g_alpha2, g_k;
+};
+template <typename T> IRB_HD void pixel_grad_zero(PixelGrad<T>& g) {
+    g.g_cx = V3<T>{0, 0, 0};
+    g.g_cy = V3<T>{0, 0, 0};
+    g.g_n = V3<T>{0, 0, 0};
+    g.G_n1 = 0;
+    g.g_alpha2 = 0;
+    g.g_k = 0;
+}
+
+// Backward of one direction.  eD = Omega_d * sum_c gD_c (A_c/pi) E_cd, eS = Omega_d * sum_c gS_c E_cd.
+template <typename T>
+IRB_HD void dir_bwd(PixelGrad<T>& g, const Pixel<T>& px, const Dir<T>& dr, T wx, T wy, T wz, T eD, T eS) {
+    T g_ndl = eD + eS * dr.spec;
+    const T g_spec = eS * dr.ndl;
+    const T inv_nom = x_rcp(dr.nom);
+    const T g_F = g_spec * px.alpha2 * inv_nom;
+    const bool nom_pass = (dr.nom_raw >= (T)1e-6) && (dr.nom_raw <= Consts<T>::FOUR_PI);
+    const T g_nom = nom_pass ? -g_spec * dr.spec * inv_nom : T(0);
+    g.g_alpha2 += g_spec * dr.F * inv_nom;
+    const T c4 = g_nom * Consts<T>::FOUR_PI;
+    const T g_n0 = c4 * T(2) * dr.n0 * px.n1 * dr.n2;
+    g.G_n1 += c4 * dr.n0 * dr.n0 * dr.n2;
+    const T g_n2 = c4 * dr.n0 * dr.n0 * px.n1;
+    const T g_ndh = g_n0 * T(2) * dr.ndh * (px.alpha2 - T(1));
+    g.g_alpha2 += g_n0 * dr.ndh * dr.ndh;
+    g_ndl += g_n2 * (T(1) - px.k);
+    g.g_k += g_n2 * (T(1) - dr.ndl);
+    const T g_g = g_F * (T(1) - px.F0) * dr.p2 * Consts<T>::LN2;
+    const T g_vdh = g_g * (T(-2 * 5.55472) * dr.vdh - T(6.98316));
+    const T g_ndhr = (dr.ndh_raw >= T(0) && dr.ndh_raw <= T(1)) ? g_ndh : T(0);
+    const V3<T> g_h{g_ndhr * px.n.x + g_vdh * px.v.x, g_ndhr * px.n.y + g_vdh * px.v.y,
+                    g_ndhr * px.n.z + g_vdh * px.v.z};
+    g.g_n = axpy(g_ndhr, dr.h, g.g_n);
+    V3<T> g_m;
+    if (dr.mm >= (T)1e-6) {
+        const T hg = dot(dr.h, g_h);
+        g_m = V3<T>{(g_h.x - dr.h.x * hg) * dr.rinv, (g_h.y - dr.h.y * hg) * dr.rinv, (g_h.z - dr.h.z * hg) * dr.rinv};
+    } else {
+        g_m = scale(dr.rinv, g_h);
+    }
+    const T g_ndlr = (dr.ndl_raw >= T(0) && dr.ndl_raw <= T(1)) ? g_ndl : T(0);
+    const V3<T> g_l{T(0.5) * g_m.x + g_ndlr * px.n.x, T(0.5) * g_m.y + g_ndlr * px.n.y, T(0.5) * g_m.z + g_ndlr * px.n.z};
+    g.g_n = axpy(g_ndlr, dr.l, g.g_n);
+    g.g_cx = axpy(wx, g_l, g.g_cx);
+    g.g_cy = axpy(wy, g_l, g.g_cy);
+    g.g_n = axpy(wz, g_l, g.g_n);
+}
+
+// After the direction loop: frame / normalisation / roughness chain.  Returns d/d(pooled normal)
+// and d/d(pooled rough).
+template <typename T>
+IRB_HD void pixel_bwd_finish(const PixelGrad<T>& g, const Pixel<T>& px, const V3<T>& nt, V3<T>& g_nt, T& g_rough) {
+    V3<T> g_n = g.g_n;
+    V3<T> g_cy = g.g_cy;
+    const T g_ndv = g.G_n1 * (T(1) - px.k);
+    const T g_k = g.g_k + g.G_n1 * (T(1) - px.ndv);
+    if (px.ndv_raw >= T(0) && px.ndv_raw <= T(1)) g_n = axpy(g_ndv, px.v, g_n);
+    // camx = -q / qn
+    V3<T> g_q;
+    if (px.q_ok) {
+        const T cg = dot(px.camx, g.g_cx);
+        g_q = V3<T>{-(g.g_cx.x - px.camx.x * cg) / px.qn, -(g.g_cx.y - px.camx.y * cg) / px.qn,
+                    -(g.g_cx.z - px.camx.z * cg) / px.qn};
+    } else {
+        g_q = scale(T(-1) / px.qn, g.g_cx);
+    }
+    // q = camy x n
+    const V3<T> t1 = cross(px.n, g_q);
+    g_cy = V3<T>{g_cy.x + t1.x, g_cy.y + t1.y, g_cy.z + t1.z};
+    const V3<T> t2 = cross(g_q, px.camy);
+    g_n = V3<T>{g_n.x + t2.x, g_n.y + t2.y, g_n.z + t2.z};
+    // camy = p / pn
+    V3<T> g_p;
+    if (px.p_ok) {
+        const T cg = dot(px.camy, g_cy);
+        g_p = V3<T>{(g_cy.x - px.camy.x * cg) / px.pn, (g_cy.y - px.camy.y * cg) / px.pn, (g_cy.z - px.camy.z * cg) / px.pn};
+    } else {
+        g_p = scale(T(1) / px.pn, g_cy);
+    }
+    // p = up - (up.n) n
+    const T ngp = dot(px.n, g_p);
+    g_n = V3<T>{g_n.x - px.un * g_p.x, g_n.y - px.un * g_p.y - ngp, g_n.z - px.un * g_p.z};
+    // n = n~ / sqrt(clamp(s))
+    if (px.s >= (T)1e-6 && px.s <= T(1)) {
+        const T ng = dot(px.n, g_n);
+        g_nt = V3<T>{(g_n.x - px.n.x * ng) * px.inv, (g_n.y - px.n.y * ng) * px.inv, (g_n.z - px.n.z * ng) * px.inv};
+    } else {
+        g_nt = scale(px.inv, g_n);
+    }
+    (void)nt;
+    const T g_rho = g.g_alpha2 * T(4) * px.rho * px.rho * px.rho + g_k * (px.rho + T(1)) * T(0.25);
+    g_rough = g_rho * T(0.5);
+}
+
+}  // namespace irb

@@ -1,0 +1,404 @@
+"""Host-side mirror of the hot-path classes of the reference's ``models.py``.
+
+Same names, constructor keywords, public attributes, method names and return values as
+``/root/reference/models.py``, so ``wrapperBRDFLight.py``, ``trainLight.py``,
+``testReal.py`` ... call them unchanged:
+
+  * ``output2env``      (models.py:348-404)  -> CUDA kernels ``irb_sg_to_env_fwd/bwd``
+  * ``renderingLayer``  (models.py:407-522)  -> ``irb_render_env_fwd/bwd`` or, when the env-map
+                                               was produced by ``output2env`` (the trainLight /
+                                               testReal call pattern), the FUSED
+                                               ``irb_render_sg_fwd/bwd`` that never reads it
+  * ``LSregress`` / ``LSregressDiffSpec`` (models.py:7-84) -- per-sample scale regressions, PyTorch
+
+Everything numeric in the two classes runs in hand-written sm_100a kernels behind the C ABI
+(include/irb.h) through ctypes; PyTorch only owns memory, streams and the autograd graph.
+There is no CPU path: CPU tensors raise.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+__all__ = ['output2env', 'renderingLayer', 'LSregress', 'LSregressDiffSpec']
+
+
+def _chk(t, name, ndim=None):
+    if not isinstance(t, torch.Tensor):
+        raise ValueError('%s must be a torch.Tensor' % name)
+    if not t.is_cuda:
+        raise ValueError('%s must be a CUDA tensor: this build has no CPU path (got device %s)' % (name, t.device))
+    if t.dtype != torch.float32:
+        raise ValueError('%s must be float32 (got %s)' % (name, t.dtype))
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError('%s must have %d dims (got shape %s)' % (name, ndim, tuple(t.shape)))
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------
+# autograd bridges to the C ABI
+# ------------------------------------------------------------------------------------------
+
+class _AvgPool(torch.autograd.Function):
+    """F.adaptive_avg_pool2d (models.py:465-469) via irb_avgpool_fwd/bwd."""
+
+    @staticmethod
+    def forward(ctx, x, R, C):
+        x = _c(x)
+        B, ch, H, W = x.shape
+        ctx.dims = (B * ch, H, W, R, C)
+        out = torch.empty(B, ch, R, C, device=x.device, dtype=x.dtype)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().irb_avgpool_fwd(_lib.ptr(x), _lib.ptr(out), B * ch, H, W, R, C,
+                                                  _lib.stream_ptr(x.device)), 'irb_avgpool_fwd')
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        N, H, W, R, C = ctx.dims
+        g = _c(g)
+        gi = torch.empty(g.shape[0], g.shape[1], H, W, device=g.device, dtype=g.dtype)
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.lib().irb_avgpool_bwd(_lib.ptr(g), _lib.ptr(gi), N, H, W, R, C,
+                                                  _lib.stream_ptr(g.device)), 'irb_avgpool_bwd')
+        return gi, None, None
+
+
+def _pool(x, R, C):
+    if x.shape[2] == R and x.shape[3] == C:
+        return x
+    return _AvgPool.apply(x, R, C)
+
+
+class _SgToEnv(torch.autograd.Function):
+    """models.py:371-404.  Returns (env, lamb_w, weight_w)."""
+
+    @staticmethod
+    def forward(ctx, axis, lamb, weight, envH, envW, warp):
+        axis, lamb, weight = _c(axis), _c(lamb), _c(weight)
+        B, K, _, R, C = axis.shape
+        dev = axis.device
+        env = torch.empty(B, 3, R, C, envH, envW, device=dev, dtype=torch.float32)
+        if warp:
+            lamb_w = torch.empty_like(lamb)
+            weight_w = torch.empty_like(weight)
+        else:
+            lamb_w = weight_w = None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().irb_sg_to_env_fwd(
+                _lib.ptr(axis), _lib.ptr(lamb), _lib.ptr(weight), _lib.ptr(env), _lib.ptr(lamb_w),
+                _lib.ptr(weight_w), B, K, R, C, envH, envW, int(warp), _lib.stream_ptr(dev)), 'irb_sg_to_env_fwd')
+        ctx.save_for_backward(axis, lamb, weight, lamb_w, weight_w)
+        ctx.cfg = (envH, envW, int(warp))
+        ctx.set_materialize_grads(False)
+        if warp:
+            return env, lamb_w, weight_w
+        return env, lamb, weight
+
+    @staticmethod
+    def backward(ctx, g_env, g_lw, g_ww):
+        axis, lamb, weight, lamb_w, weight_w = ctx.saved_tensors
+        envH, envW, warp = ctx.cfg
+        B, K, _, R, C = axis.shape
+        dev = axis.device
+        need = ctx.needs_input_grad
+        g_axis = g_lamb = g_weight = None
+        if g_env is not None and any(need[:3]):
+            g_env = _c(g_env)
+            g_axis = torch.empty_like(axis) if need[0] else None
+            g_lamb = torch.empty_like(lamb) if need[1] else None
+            g_weight = torch.empty_like(weight) if need[2] else None
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().irb_sg_to_env_bwd(
+                    _lib.ptr(axis), _lib.ptr(lamb), _lib.ptr(weight), _lib.ptr(g_env), _lib.ptr(g_axis),
+                    _lib.ptr(g_lamb), _lib.ptr(g_weight), B, K, R, C, envH, envW, warp, _lib.stream_ptr(dev)),
+                    'irb_sg_to_env_bwd')
+        # gradients arriving through the (rarely used) warped lamb / weight outputs
+        cw = np.pi / 2 * 0.999
+        if g_lw is not None and need[1]:
+            t = g_lw * (cw * (1 + lamb_w * lamb_w)) if warp else g_lw
+            g_lamb = t if g_lamb is None else g_lamb + t
+        if g_ww is not None and need[2]:
+            t = g_ww * (cw * (1 + weight_w * weight_w)) if warp else g_ww
+            g_weight = t if g_weight is None else g_weight + t
+        return g_axis, g_lamb, g_weight, None, None, None
+
+
+class _RenderEnv(torch.autograd.Function):
+    """models.py:466-520 on pooled maps and a materialised env-map."""
+
+    @staticmethod
+    def forward(ctx, albedo, normal, rough, env, view, F0):
+        albedo, normal, rough, env = _c(albedo), _c(normal), _c(rough), _c(env)
+        B, _, R, C, envH, envW = env.shape
+        dev = env.device
+        od = torch.empty(B, 3, R, C, device=dev, dtype=torch.float32)
+        os_ = torch.empty_like(od)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().irb_render_env_fwd(
+                _lib.ptr(albedo), _lib.ptr(normal), _lib.ptr(rough), _lib.ptr(env), _lib.ptr(view), _lib.ptr(od),
+                _lib.ptr(os_), B, R, C, envH, envW, float(F0), _lib.stream_ptr(dev)), 'irb_render_env_fwd')
+        ctx.save_for_backward(albedo, normal, rough, env, view)
+        ctx.F0 = float(F0)
+        return od, os_
+
+    @staticmethod
+    def backward(ctx, g_d, g_s):
+        albedo, normal, rough, env, view = ctx.saved_tensors
+        B, _, R, C, envH, envW = env.shape
+        dev = env.device
+        need = ctx.needs_input_grad
+        g_d = _c(g_d) if g_d is not None else torch.zeros(B, 3, R, C, device=dev)
+        g_s = _c(g_s) if g_s is not None else torch.zeros(B, 3, R, C, device=dev)
+        ga = torch.empty_like(albedo) if need[0] else None
+        gn = torch.empty_like(normal) if need[1] else None
+        gr = torch.empty_like(rough) if need[2] else None
+        ge = torch.empty_like(env) if need[3] else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().irb_render_env_bwd(
+                _lib.ptr(albedo), _lib.ptr(normal), _lib.ptr(rough), _lib.ptr(env), _lib.ptr(view), _lib.ptr(g_d),
+                _lib.ptr(g_s), _lib.ptr(ga), _lib.ptr(gn), _lib.ptr(gr), _lib.ptr(ge), B, R, C, envH, envW, ctx.F0,
+                _lib.stream_ptr(dev)), 'irb_render_env_bwd')
+        return ga, gn, gr, ge, None, None
+
+
+class _RenderSG(torch.autograd.Function):
+    """Fused output2env + forwardEnv (wrapperBRDFLight.py:177,194) on pooled maps."""
+
+    @staticmethod
+    def forward(ctx, albedo, normal, rough, axis, lamb, weight, view, F0, envH, envW, warp):
+        albedo, normal, rough = _c(albedo), _c(normal), _c(rough)
+        axis, lamb, weight = _c(axis), _c(lamb), _c(weight)
+        B, K, _, R, C = axis.shape
+        dev = axis.device
+        od = torch.empty(B, 3, R, C, device=dev, dtype=torch.float32)
+        os_ = torch.empty_like(od)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().irb_render_sg_fwd(
+                _lib.ptr(albedo), _lib.ptr(normal), _lib.ptr(rough), _lib.ptr(axis), _lib.ptr(lamb),
+                _lib.ptr(weight), _lib.ptr(view), _lib.ptr(od), _lib.ptr(os_), B, K, R, C, envH, envW, float(F0),
+                int(warp), _lib.stream_ptr(dev)), 'irb_render_sg_fwd')
+        ctx.save_for_backward(albedo, normal, rough, axis, lamb, weight, view)
+        ctx.cfg = (float(F0), envH, envW, int(warp))
+        return od, os_
+
+    @staticmethod
+    def backward(ctx, g_d, g_s):
+        albedo, normal, rough, axis, lamb, weight, view = ctx.saved_tensors
+        F0, envH, envW, warp = ctx.cfg
+        B, K, _, R, C = axis.shape
+        dev = axis.device
+        need = ctx.needs_input_grad
+        g_d = _c(g_d) if g_d is not None else torch.zeros(B, 3, R, C, device=dev)
+        g_s = _c(g_s) if g_s is not None else torch.zeros(B, 3, R, C, device=dev)
+        outs = [torch.empty_like(t) if need[i] else None
+                for i, t in enumerate((albedo, normal, rough, axis, lamb, weight))]
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().irb_render_sg_bwd(
+                _lib.ptr(albedo), _lib.ptr(normal), _lib.ptr(rough), _lib.ptr(axis), _lib.ptr(lamb),
+                _lib.ptr(weight), _lib.ptr(view), _lib.ptr(g_d), _lib.ptr(g_s), *[_lib.ptr(o) for o in outs],
+                B, K, R, C, envH, envW, F0, warp, _lib.stream_ptr(dev)), 'irb_render_sg_bwd')
+        return tuple(outs) + (None, None, None, None, None)
+
+
+# ------------------------------------------------------------------------------------------
+# public classes (reference names)
+# ------------------------------------------------------------------------------------------
+
+def _direction_table(envWidth, envHeight):
+    """ls[d] = (sinEl cosAz, sinEl sinAz, cosEl), d = i*envWidth + j (models.py:353-362, 437-446)."""
+    az = ((np.arange(envWidth) + 0.5) / envWidth - 0.5) * 2 * np.pi
+    el = ((np.arange(envHeight) + 0.5) / envHeight) * np.pi / 2.0
+    az, el = np.meshgrid(az, el)
+    return np.sin(el) * np.cos(az), np.sin(el) * np.sin(az), np.cos(el), el
+
+
+class output2env():
+    """SG lobes -> env-map.  Mirror of models.output2env (models.py:348-404)."""
+
+    MAX_FUSED_LOBES = 24
+
+    def __init__(self, SGNum, envWidth=16, envHeight=8, isCuda=True):
+        self.envWidth = envWidth
+        self.envHeight = envHeight
+        lx, ly, lz, _ = _direction_table(envWidth, envHeight)
+        ls = np.stack([lx, ly, lz], axis=0)[np.newaxis, np.newaxis, :, np.newaxis, np.newaxis, :, :]
+        self.ls = torch.from_numpy(ls.astype(np.float32))
+        self.SGNum = SGNum
+        self.isCuda = isCuda
+        if isCuda:
+            self.ls = self.ls.cuda()
+        self.ls.requires_grad = False
+
+    def _check(self, axis, lamb, weight):
+        _chk(axis, 'axis', 5)
+        _chk(lamb, 'lamb', 4)
+        _chk(weight, 'weight', 4)
+        B, K, three, R, C = axis.shape
+        if K != self.SGNum or three != 3:
+            raise ValueError('axis must be [B,%d,3,R,C] (got %s)' % (self.SGNum, tuple(axis.shape)))
+        if tuple(lamb.shape) != (B, K, R, C):
+            raise ValueError('lamb must be [B,SGNum,R,C] = %s (got %s)' % ((B, K, R, C), tuple(lamb.shape)))
+        if tuple(weight.shape) != (B, 3 * K, R, C):
+            raise ValueError('weight must be [B,3*SGNum,R,C] = %s (got %s)' % ((B, 3 * K, R, C), tuple(weight.shape)))
+        if lamb.device != axis.device or weight.device != axis.device:
+            raise ValueError('axis / lamb / weight must live on one device')
+
+    def fromSGtoIm(self, axis, lamb, weight):
+        """models.py:371-389: lamb / weight already warped.  Returns envmaps [B,3,R,C,envH,envW]."""
+        self._check(axis, lamb, weight)
+        env, _, _ = _SgToEnv.apply(axis, lamb, weight, self.envHeight, self.envWidth, False)
+        return env
+
+    def output2env(self, axisOrig, lambOrig, weightOrig):
+        """models.py:391-404.  Returns (envmaps, axis, lamb, weight) like the reference.
+
+        The returned env-map remembers the SG parameters it came from, so that
+        ``renderingLayer.forwardEnv`` can take the fused kernel (the env-map is then never re-read).
+        """
+        self._check(axisOrig, lambOrig, weightOrig)
+        env, lamb, weight = _SgToEnv.apply(axisOrig, lambOrig, weightOrig, self.envHeight, self.envWidth, True)
+        if self.SGNum <= self.MAX_FUSED_LOBES:
+            env._irb_sg = (axisOrig, lambOrig, weightOrig, self.envHeight, self.envWidth)
+        return env, axisOrig, lamb, weight
+
+
+class renderingLayer():
+    """SG-lit microfacet shading.  Mirror of models.renderingLayer (models.py:407-522)."""
+
+    def __init__(self, imWidth=160, imHeight=120, fov=57, F0=0.05, cameraPos=[0, 0, 0],
+                 envWidth=16, envHeight=8, isCuda=True):
+        self.imHeight = imHeight
+        self.imWidth = imWidth
+        self.envWidth = envWidth
+        self.envHeight = envHeight
+        self.fov = fov / 180.0 * np.pi
+        self.F0 = F0
+        self.cameraPos = np.array(cameraPos, dtype=np.float32).reshape([1, 3, 1, 1])
+        self.xRange = 1 * np.tan(self.fov / 2)
+        self.yRange = float(imHeight) / float(imWidth) * self.xRange
+        self.isCuda = isCuda
+        # pixel centres on the z=-1 plane, y up (models.py:421-426); unit view vectors (:428-430)
+        xs = np.linspace(-self.xRange, self.xRange, imWidth)
+        ys = np.linspace(-self.yRange, self.yRange, imHeight)[::-1]
+        gx, gy = np.meshgrid(xs, ys)
+        pc = np.stack([gx, gy, -np.ones((imHeight, imWidth), dtype=np.float32)]).astype(np.float32)[np.newaxis]
+        vv = self.cameraPos - pc
+        vv = (vv / np.sqrt(np.maximum(np.sum(vv * vv, axis=1), 1e-12)[:, np.newaxis, :, :])).astype(np.float32)
+        self.v = torch.from_numpy(vv)
+        self.pCoord = torch.from_numpy(pc)
+        self.up = torch.Tensor([0, 1, 0])
+        lx, ly, lz, el = _direction_table(envWidth, envHeight)
+        ls = np.stack([lx.reshape(-1), ly.reshape(-1), lz.reshape(-1)], axis=1)
+        ew = np.sin(el.reshape(-1, 1)) * np.pi * np.pi / envWidth / envHeight
+        self.ls = torch.from_numpy(ls.astype(np.float32))
+        self.envWeight = torch.from_numpy(ew.astype(np.float32)).unsqueeze(0).unsqueeze(-1).unsqueeze(-1)
+        if isCuda:
+            self.v = self.v.cuda()
+            self.pCoord = self.pCoord.cuda()
+            self.up = self.up.cuda()
+            self.ls = self.ls.cuda()
+            self.envWeight = self.envWeight.cuda()
+
+    # -- helpers -----------------------------------------------------------------------------
+    def _view(self, dev):
+        v = self.v
+        if v.device != dev:
+            v = v.to(dev)
+            self.v = v
+        return v.reshape(3, self.imHeight, self.imWidth)
+
+    def _check_maps(self, diffusePred, normalPred, roughPred, R, C):
+        _chk(diffusePred, 'diffusePred', 4)
+        _chk(normalPred, 'normalPred', 4)
+        _chk(roughPred, 'roughPred', 4)
+        B = diffusePred.shape[0]
+        if diffusePred.shape[1] != 3 or normalPred.shape[1] != 3 or roughPred.shape[1] != 1:
+            raise ValueError('diffusePred / normalPred / roughPred must have 3 / 3 / 1 channels')
+        if normalPred.shape[0] != B or roughPred.shape[0] != B:
+            raise ValueError('batch sizes differ')
+        if (R, C) != (self.imHeight, self.imWidth):
+            raise ValueError('env grid %dx%d does not match the layer (imHeight=%d, imWidth=%d)'
+                             % (R, C, self.imHeight, self.imWidth))
+
+    # -- reference API -------------------------------------------------------------------------
+    def forwardEnv(self, diffusePred, normalPred, roughPred, envmap):
+        """models.py:461-522.  Returns (colorDiffuse, colorSpec), each [B,3,R,C]."""
+        _chk(envmap, 'envmap', 6)
+        B, three, R, C, envH, envW = envmap.shape
+        if three != 3 or (envH, envW) != (self.envHeight, self.envWidth):
+            raise ValueError('envmap must be [B,3,R,C,%d,%d] (got %s)' % (self.envHeight, self.envWidth,
+                                                                            tuple(envmap.shape)))
+        self._check_maps(diffusePred, normalPred, roughPred, R, C)
+        sg = getattr(envmap, '_irb_sg', None)
+        if sg is not None and sg[3] == envH and sg[4] == envW:
+            return self.forwardSG(diffusePred, normalPred, roughPred, sg[0], sg[1], sg[2])
+        dev = envmap.device
+        A = _pool(diffusePred, R, C)
+        N = _pool(normalPred, R, C)
+        Rg = _pool(roughPred, R, C)
+        return _RenderEnv.apply(A, N, Rg, envmap, self._view(dev), self.F0)
+
+    # -- fused entry point (superset of the reference API) -------------------------------------
+    def forwardSG(self, diffusePred, normalPred, roughPred, axisOrig, lambOrig, weightOrig, warp=True):
+        """output2env.output2env + forwardEnv in ONE kernel; the env-map is never materialised.
+
+        axisOrig [B,K,3,R,C], lambOrig [B,K,R,C], weightOrig [B,3K,R,C] are the raw LightNet
+        outputs (``warp=True`` applies tan(pi/2*0.999*x), models.py:396-400)."""
+        _chk(axisOrig, 'axisOrig', 5)
+        _chk(lambOrig, 'lambOrig', 4)
+        _chk(weightOrig, 'weightOrig', 4)
+        B, K, _, R, C = axisOrig.shape
+        self._check_maps(diffusePred, normalPred, roughPred, R, C)
+        dev = axisOrig.device
+        A = _pool(diffusePred, R, C)
+        N = _pool(normalPred, R, C)
+        Rg = _pool(roughPred, R, C)
+        return _RenderSG.apply(A, N, Rg, axisOrig, lambOrig, weightOrig, self._view(dev), self.F0,
+                               self.envHeight, self.envWidth, warp)
+
+
+# ------------------------------------------------------------------------------------------
+# scale-ambiguity regressions (models.py:7-84) -- PyTorch (per-sample reductions)
+# ------------------------------------------------------------------------------------------
+
+def LSregress(pred, gt, origin):
+    """Per-sample least-squares scale mapping pred onto gt, applied to origin (models.py:7-21)."""
+    nb = pred.size(0)
+    p = pred.reshape(nb, -1)
+    g = gt.reshape(nb, -1)
+    coef = (torch.sum(p * g, dim=1) / torch.clamp(torch.sum(p * p, dim=1), min=1e-5)).detach()
+    coef = torch.clamp(coef, 0.001, 1000)
+    return origin * coef.view([nb] + [1] * (origin.dim() - 1))
+
+
+def LSregressDiffSpec(diff, spec, imOrig, diffOrig, specOrig):
+    """Two-coefficient (diffuse, specular) per-sample regression with diffuse-only fallback, then a
+    second scalar fit of clamp(d+s,0,1) to the image (models.py:23-84)."""
+    nb, nc, nh, nw = diff.size()
+    mask = (imOrig < 0.9).float()
+    d = (diff * mask).view(nb, -1)
+    s = (spec * mask).view(nb, -1)
+    im = (imOrig * mask).view(nb, -1)
+    a11 = torch.sum(d * d, dim=1)
+    a22 = torch.sum(s * s, dim=1)
+    a12 = torch.sum(d * s, dim=1)
+    det = a11 * a22 - a12 * a12
+    b1 = torch.sum(d * im, dim=1)
+    b2 = torch.sum(s * im, dim=1)
+    c_d = (b1 * a22 - b2 * a12) / torch.clamp(det, min=1e-2)
+    c_s = (-b1 * a12 + a11 * b2) / torch.clamp(det, min=1e-2)
+    c_d_only = torch.clamp(b1 / torch.clamp(a11, min=1e-5), 0.001, 1000)
+    ok = ((det / (nc * nh * nw)).detach() > 1e-2).float()
+    coefD = torch.clamp(ok * c_d + (1 - ok) * c_d_only, min=0, max=1000).view(nb, 1, 1, 1)
+    coefS = torch.clamp(ok * c_s, min=0, max=1000).view(nb, 1, 1, 1)
+    dS = coefD * diffOrig
+    sS = coefS * specOrig
+    r = torch.clamp(dS + sS, 0, 1).view(nb, -1)
+    io = imOrig.view(nb, -1)
+    coefIm = (torch.sum(r * io, dim=1) / torch.clamp(torch.sum(r * r, dim=1), min=1e-5)).detach()
+    coefIm = torch.clamp(coefIm, 0.001, 1000).view(nb, 1, 1, 1)
+    return coefIm * dS, coefIm * sS

@@ -111,11 +111,12 @@ def _normalize(x, dim, eps=1e-12):
     return x / x.norm(dim=dim, keepdim=True).clamp_min(eps)
 
 
-def render_env(albedo, normal, rough, envmap, fov=57.0, F0=0.05, cameraPos=(0.0, 0.0, 0.0)):
+def render_env(albedo, normal, rough, envmap, fov=57.0, F0=0.05, cameraPos=(0.0, 0.0, 0.0), view=None):
     """colorDiffuse, colorSpec [B,3,R,C] of models.py:461-522.
 
     albedo/normal [B,3,H,W], rough [B,1,H,W] are pooled to the env grid R x C
-    (models.py:465-469); envmap [B,3,R,C,envH,envW].
+    (models.py:465-469); envmap [B,3,R,C,envH,envW].  ``view`` optionally overrides the
+    per-pixel view vectors [3,R,C] (used to render a crop of a larger frame).
     """
     dt = envmap.dtype
     B = albedo.shape[0]
@@ -125,7 +126,7 @@ def render_env(albedo, normal, rough, envmap, fov=57.0, F0=0.05, cameraPos=(0.0,
     ls_np, ew_np = env_table(envH, envW)
     ls = torch.from_numpy(ls_np).to(dt)
     ew = torch.from_numpy(ew_np).to(dt)
-    v = torch.from_numpy(camera_rays(R, C, fov, cameraPos)).to(dt)  # [3,R,C]
+    v = (torch.from_numpy(camera_rays(R, C, fov, cameraPos)) if view is None else view).to(dt)  # [3,R,C]
 
     # models.py:465-469
     A = F.adaptive_avg_pool2d(albedo, (R, C))

@@ -1,0 +1,65 @@
+// hostcheck.cpp -- TEST INFRASTRUCTURE.  Instantiates the per-pixel drivers of
+// inverserenderingofindoorscene_b200/csrc/*.cuh on the HOST (float and double) so that the
+// shading math and the hand-derived backward can be checked against the oracle in a container
+// without a GPU.  Never linked into the product library; loaded only by tests/.
+#include "../../inverserenderingofindoorscene_b200/csrc/irb_driver_env.cuh"
+
+using namespace irb;
+
+template <int KC, typename F> static void for_pixels(int B, int R, int C, F f) {
+    for (size_t b = 0; b < (size_t)B; ++b)
+        for (size_t p = 0; p < (size_t)R * C; ++p) f(b, p);
+}
+
+extern "C" {
+
+int hc_render_sg_fwd(int dbl, const RenderSgArgs* a, const EnvTab* tab) {
+    const int kc = a->K <= 12 ? 12 : 24;
+    for_pixels<0>(a->B, a->R, a->C, [&](size_t b, size_t p) {
+        if (dbl) { if (kc == 12) drv_render_sg_fwd<double, 12>(*a, *tab, b, p); else drv_render_sg_fwd<double, 24>(*a, *tab, b, p); }
+        else     { if (kc == 12) drv_render_sg_fwd<float, 12>(*a, *tab, b, p);  else drv_render_sg_fwd<float, 24>(*a, *tab, b, p); }
+    });
+    return 0;
+}
+
+int hc_render_sg_bwd(int dbl, const RenderSgArgs* a, const EnvTab* tab) {
+    if (a->K > 24) return -2;
+    for_pixels<0>(a->B, a->R, a->C, [&](size_t b, size_t p) {
+        if (a->K <= 12) {
+            if (dbl) drv_render_sg_bwd<double, 12, 12, true, true>(*a, *tab, b, p);
+            else drv_render_sg_bwd<float, 12, 12, true, true>(*a, *tab, b, p);
+        } else {
+            if (dbl) drv_render_sg_bwd<double, 24, 12, true, true>(*a, *tab, b, p);
+            else drv_render_sg_bwd<float, 24, 12, true, true>(*a, *tab, b, p);
+        }
+    });
+    return 0;
+}
+
+int hc_sg_to_env_fwd(int dbl, const SgEnvArgs* s, const EnvTab* tab) {
+    for_pixels<0>(s->B, s->R, s->C, [&](size_t b, size_t p) {
+        if (dbl) drv_sg_to_env_fwd<double, 12>(*s, *tab, b, p); else drv_sg_to_env_fwd<float, 12>(*s, *tab, b, p);
+    });
+    return 0;
+}
+int hc_sg_to_env_bwd(int dbl, const SgEnvArgs* s, const EnvTab* tab) {
+    for_pixels<0>(s->B, s->R, s->C, [&](size_t b, size_t p) {
+        if (dbl) drv_sg_to_env_bwd<double, 12>(*s, *tab, b, p); else drv_sg_to_env_bwd<float, 12>(*s, *tab, b, p);
+    });
+    return 0;
+}
+int hc_render_env_fwd(int dbl, const RenderEnvArgs* s, const EnvTab* tab) {
+    for_pixels<0>(s->B, s->R, s->C, [&](size_t b, size_t p) {
+        if (dbl) drv_render_env_fwd<double>(*s, *tab, b, p); else drv_render_env_fwd<float>(*s, *tab, b, p);
+    });
+    return 0;
+}
+int hc_render_env_bwd(int dbl, const RenderEnvArgs* s, const EnvTab* tab) {
+    for_pixels<0>(s->B, s->R, s->C, [&](size_t b, size_t p) {
+        if (dbl) drv_render_env_bwd<double>(*s, *tab, b, p); else drv_render_env_bwd<float>(*s, *tab, b, p);
+    });
+    return 0;
+}
+size_t hc_sizeof_render_sg_args() { return sizeof(RenderSgArgs); }
+size_t hc_sizeof_envtab() { return sizeof(EnvTab); }
+}

@@ -1,0 +1,95 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds for sm_100a, loads, and exports
+every symbol include/irb.h declares; the host mirror keeps the reference's API surface; CPU tensors
+are refused loudly (no CPU fallback).  No compute calls: there is no GPU in this container."""
+import ctypes
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope='module')
+def built():
+    from inverserenderingofindoorscene_b200 import _build
+    return _build.build()
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, 'include', 'irb.h')).read()
+    declared = sorted(set(re.findall(r'\b(irb_[a-z0-9_]+)\s*\(', hdr)))
+    assert len(declared) >= 15
+    lib = ctypes.CDLL(built)
+    for name in declared:
+        assert hasattr(lib, name), name
+    from inverserenderingofindoorscene_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared
+    h = _lib.lib()
+    assert h.irb_abi_version() == 1
+
+
+def test_sass_is_sm100a_only(built):
+    import subprocess
+    out = subprocess.run(['cuobjdump', '-lelf', built], capture_output=True, text=True).stdout
+    archs = set(re.findall(r'sm_(\d+a?)', out))
+    assert archs == {'100a'}, archs
+
+
+def test_reference_api_surface():
+    from inverserenderingofindoorscene_b200 import models
+    sig = inspect.signature(models.renderingLayer.__init__)
+    assert list(sig.parameters)[1:] == ['imWidth', 'imHeight', 'fov', 'F0', 'cameraPos', 'envWidth', 'envHeight', 'isCuda']
+    assert [p.default for p in list(sig.parameters.values())[1:]] == [160, 120, 57, 0.05, [0, 0, 0], 16, 8, True]
+    sig = inspect.signature(models.output2env.__init__)
+    assert list(sig.parameters)[1:] == ['SGNum', 'envWidth', 'envHeight', 'isCuda']
+    assert list(inspect.signature(models.renderingLayer.forwardEnv).parameters)[1:] == \
+        ['diffusePred', 'normalPred', 'roughPred', 'envmap']
+    assert list(inspect.signature(models.output2env.output2env).parameters)[1:] == ['axisOrig', 'lambOrig', 'weightOrig']
+    assert list(inspect.signature(models.output2env.fromSGtoIm).parameters)[1:] == ['axis', 'lamb', 'weight']
+    rl = models.renderingLayer(imWidth=16, imHeight=12, isCuda=False)
+    for a in ('v', 'pCoord', 'up', 'ls', 'envWeight', 'fov', 'F0', 'xRange', 'yRange', 'imHeight', 'imWidth',
+              'envHeight', 'envWidth', 'isCuda', 'cameraPos'):
+        assert hasattr(rl, a), a
+    assert tuple(rl.v.shape) == (1, 3, 12, 16) and tuple(rl.ls.shape) == (128, 3)
+    assert tuple(rl.envWeight.shape) == (1, 128, 1, 1, 1)
+    o = models.output2env(12, isCuda=False)
+    assert tuple(o.ls.shape) == (1, 1, 3, 1, 1, 8, 16)
+
+
+def test_constants_match_reference_fixture(golden_dir):
+    import numpy as np
+    from inverserenderingofindoorscene_b200 import models
+    from oracle import render_oracle as ro
+    z = np.load(os.path.join(golden_dir, 'render_pool2_full.npz'))
+    B, H, W, R, C, K = [int(x) for x in z['meta']]
+    rl = models.renderingLayer(imWidth=C, imHeight=R, isCuda=False)
+    assert np.array_equal(rl.v.numpy(), z['v'])          # bit-exact view vectors (models.py:428-432)
+    ls, ew = ro.env_table()
+    assert np.array_equal(rl.ls.numpy(), ls) and np.array_equal(rl.envWeight.numpy().reshape(-1), ew)
+
+
+def test_cpu_tensors_are_refused():
+    from inverserenderingofindoorscene_b200 import models
+    rl = models.renderingLayer(imWidth=8, imHeight=6, isCuda=False)
+    o = models.output2env(12, isCuda=False)
+    with pytest.raises(ValueError, match='no CPU path'):
+        o.output2env(torch.zeros(1, 12, 3, 6, 8), torch.zeros(1, 12, 6, 8), torch.zeros(1, 36, 6, 8))
+    with pytest.raises(ValueError, match='no CPU path'):
+        rl.forwardEnv(torch.zeros(1, 3, 6, 8), torch.zeros(1, 3, 6, 8), torch.zeros(1, 1, 6, 8),
+                      torch.zeros(1, 3, 6, 8, 8, 16))
+
+
+def test_lsregress_matches_golden(golden_dir):
+    import numpy as np
+    from inverserenderingofindoorscene_b200 import models
+    from conftest import relerr
+    z = np.load(os.path.join(golden_dir, 'render_pool2_full.npz'))
+    d64, s64 = torch.from_numpy(z['ref64_diff']), torch.from_numpy(z['ref64_spec'])
+    # float() mask inside LSregressDiffSpec forces fp32 there; run the product code in fp32
+    dS, sS = models.LSregressDiffSpec(d64.float(), s64.float(), torch.from_numpy(z['im']), d64.float(), s64.float())
+    assert relerr(dS.numpy(), z['lsreg_diff']) <= 1e-5 and relerr(sS.numpy(), z['lsreg_spec']) <= 1e-5
+    e = torch.from_numpy(z['ref64_env'])
+    assert relerr(models.LSregress(e * 0.5, e + 0.1, e).numpy(), z['lsreg_env']) <= 1e-12

@@ -1,0 +1,122 @@
+"""The per-pixel math of the CUDA kernels (csrc/irb_*.cuh), instantiated on the HOST in double
+and float by tests/hostcheck, against the reference-generated golden fixtures.  This checks the
+hand-derived backward and the E-free algebra of the fused kernel without a GPU; the -m gpu tests
+repeat the comparison through the real C ABI on the device."""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import hostcheck_lib as hc
+from conftest import GOLDEN, relerr
+from oracle import render_oracle as ro
+
+RENDER = sorted(glob.glob(os.path.join(GOLDEN, 'render_*.npz')))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    return hc.load()
+
+
+def _pooled(z):
+    B, H, W, R, Cc, K = [int(x) for x in z['meta']]
+    pool = lambda a: F.adaptive_avg_pool2d(torch.from_numpy(a).double(), (R, Cc)).float().numpy().copy()
+    return pool(z['albedo']), pool(z['normal']), pool(z['rough'])
+
+
+def _pool_bwd(g, z, H, W):
+    """push a grid-resolution gradient through adaptive_avg_pool2d (autograd of models.py:465-469)"""
+    x = torch.zeros(g.shape[0], g.shape[1], H, W, dtype=torch.float64, requires_grad=True)
+    y = F.adaptive_avg_pool2d(x, g.shape[2:])
+    return torch.autograd.grad((y * torch.from_numpy(g).double()).sum(), x)[0].numpy()
+
+
+@pytest.mark.parametrize('path', RENDER, ids=[os.path.basename(q) for q in RENDER])
+@pytest.mark.parametrize('dbl', [1, 0])
+def test_fused_render_math(lib, path, dbl):
+    z = dict(np.load(path))  # materialise: ctypes pointers must outlive the call
+    B, H, W, R, Cc, K = [int(x) for x in z['meta']]
+    ls, ew = ro.env_table()
+    tab = hc.make_tab(ls, ew)
+    alb, nrm, rg = _pooled(z)
+    view = np.ascontiguousarray(z['v'][0])
+    axis, lamb, weight = z['axis'], z['lamb'], z['weight']
+    od = np.zeros((B, 3, R, Cc), np.float32)
+    os_ = np.zeros_like(od)
+    g_alb, g_nrm = np.zeros_like(od), np.zeros_like(od)
+    g_rg = np.zeros((B, 1, R, Cc), np.float32)
+    g_ax, g_lam, g_wt = np.zeros_like(axis), np.zeros_like(lamb), np.zeros_like(weight)
+    a = hc.RenderSgArgs(hc.p(alb), hc.p(nrm), hc.p(rg), hc.p(axis), hc.p(lamb), hc.p(weight), hc.p(view),
+                        hc.p(od), hc.p(os_), hc.p(z['gD']), hc.p(z['gS']), hc.p(g_alb), hc.p(g_nrm), hc.p(g_rg),
+                        hc.p(g_ax), hc.p(g_lam), hc.p(g_wt), B, K, R, Cc, 0.05, 1)
+    assert lib.hc_render_sg_fwd(dbl, C.byref(a), C.byref(tab)) == 0
+    assert lib.hc_render_sg_bwd(dbl, C.byref(a), C.byref(tab)) == 0
+    # double instantiation: only the fp32 rounding of the pooled inputs / stored outputs remains.
+    # float instantiation: SURVEY 8c protocol, e <= max(1e-4, 2 e_ref32)
+    def tol(key):
+        if dbl:
+            return 2e-6
+        e_ref = relerr(z['ref32_' + key], z['ref64_' + key])
+        return max(1e-4, 2 * e_ref)
+    assert relerr(od, z['ref64_diff']) <= tol('diff')
+    assert relerr(os_, z['ref64_spec']) <= tol('spec')
+    assert relerr(g_ax, z['ref64_g_axis']) <= tol('g_axis')
+    assert relerr(g_lam, z['ref64_g_lamb']) <= tol('g_lamb')
+    assert relerr(g_wt, z['ref64_g_weight']) <= tol('g_weight')
+    assert relerr(_pool_bwd(g_alb, z, H, W), z['ref64_g_albedo']) <= tol('g_albedo')
+    assert relerr(_pool_bwd(g_nrm, z, H, W), z['ref64_g_normal']) <= tol('g_normal')
+    assert relerr(_pool_bwd(g_rg, z, H, W), z['ref64_g_rough']) <= tol('g_rough')
+
+
+@pytest.mark.parametrize('path', RENDER[:3], ids=[os.path.basename(q) for q in RENDER[:3]])
+@pytest.mark.parametrize('dbl', [1, 0])
+def test_unfused_math(lib, path, dbl):
+    z = dict(np.load(path))  # materialise: ctypes pointers must outlive the call
+    B, H, W, R, Cc, K = [int(x) for x in z['meta']]
+    ls, ew = ro.env_table()
+    tab = hc.make_tab(ls, ew)
+    alb, nrm, rg = _pooled(z)
+    view = np.ascontiguousarray(z['v'][0])
+    axis, lamb, weight = z['axis'], z['lamb'], z['weight']
+    env = np.zeros((B, 3, R, Cc, 8, 16), np.float32)
+    lw, ww = np.zeros_like(lamb), np.zeros_like(weight)
+    g_env_in = np.ascontiguousarray(z['ref64_g_env'].astype(np.float32))
+    g_ax, g_lam, g_wt = np.zeros_like(axis), np.zeros_like(lamb), np.zeros_like(weight)
+    s = hc.SgEnvArgs(hc.p(axis), hc.p(lamb), hc.p(weight), hc.p(env), hc.p(lw), hc.p(ww), hc.p(g_env_in),
+                     hc.p(g_ax), hc.p(g_lam), hc.p(g_wt), B, K, R, Cc, 1)
+    assert lib.hc_sg_to_env_fwd(dbl, C.byref(s), C.byref(tab)) == 0
+    assert lib.hc_sg_to_env_bwd(dbl, C.byref(s), C.byref(tab)) == 0
+    t = 2e-6 if dbl else 1e-4
+    assert relerr(env, z['ref64_env']) <= max(t, 2 * relerr(z['ref32_env'], z['ref64_env']) * (1 - dbl))
+    assert relerr(lw, z['ref64_lam_w']) <= t and relerr(ww, z['ref64_wt_w']) <= t
+    # the SG grads through g_env (render-side gradient of the reference) equal the full SG grads
+    for got, key in ((g_ax, 'g_axis'), (g_lam, 'g_lamb'), (g_wt, 'g_weight')):
+        e_ref = relerr(z['ref32_' + key], z['ref64_' + key])
+        assert relerr(got, z['ref64_' + key]) <= (2e-6 if dbl else max(1e-4, 2 * e_ref)), key
+    # render_env on the reference's own fp64 env (rounded to fp32)
+    env_in = np.ascontiguousarray(z['ref64_env'].astype(np.float32))
+    od = np.zeros((B, 3, R, Cc), np.float32)
+    os_ = np.zeros_like(od)
+    g_alb, g_nrm = np.zeros_like(od), np.zeros_like(od)
+    g_rg = np.zeros((B, 1, R, Cc), np.float32)
+    g_env = np.zeros_like(env_in)
+    r = hc.RenderEnvArgs(hc.p(alb), hc.p(nrm), hc.p(rg), hc.p(env_in), hc.p(view), hc.p(od), hc.p(os_),
+                         hc.p(z['gD']), hc.p(z['gS']), hc.p(g_alb), hc.p(g_nrm), hc.p(g_rg), hc.p(g_env),
+                         B, R, Cc, 0.05)
+    assert lib.hc_render_env_fwd(dbl, C.byref(r), C.byref(tab)) == 0
+    assert lib.hc_render_env_bwd(dbl, C.byref(r), C.byref(tab)) == 0
+    def tol(key):
+        if dbl:
+            return 2e-6
+        return max(1e-4, 2 * relerr(z['ref32_' + key], z['ref64_' + key]))
+    assert relerr(od, z['ref64_diff']) <= tol('diff')
+    assert relerr(os_, z['ref64_spec']) <= tol('spec')
+    assert relerr(g_env, z['ref64_g_env']) <= tol('g_env')
+    assert relerr(_pool_bwd(g_alb, z, H, W), z['ref64_g_albedo']) <= tol('g_albedo')
+    assert relerr(_pool_bwd(g_nrm, z, H, W), z['ref64_g_normal']) <= tol('g_normal')
+    assert relerr(_pool_bwd(g_rg, z, H, W), z['ref64_g_rough']) <= tol('g_rough')

@@ -1,0 +1,214 @@
+"""GPU parity tests of the render path, through the public API (models.py mirror -> ctypes -> C ABI
+-> sm_100a kernels).  Protocol: inf-norm-normalised error against the fp64 reference
+run; pass iff e_ours <= max(1e-4, 2*e_ref32) where e_ref32 is the reference's own fp32 error."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, relerr
+
+pytestmark = pytest.mark.gpu
+
+RENDER = sorted(glob.glob(os.path.join(GOLDEN, 'render_*.npz')))
+
+
+@pytest.fixture(scope='module')
+def irb():
+    from inverserenderingofindoorscene_b200 import models, _lib
+    _lib.lib()
+    assert torch.cuda.is_available()
+    return models
+
+
+def _run(irb, z, fused):
+    B, H, W, R, C, K = [int(x) for x in z['meta']]
+    dev = torch.device('cuda')
+    ins = [torch.from_numpy(z[k]).to(dev).requires_grad_(True)
+           for k in ('albedo', 'normal', 'rough', 'axis', 'lamb', 'weight')]
+    rl = irb.renderingLayer(imWidth=C, imHeight=R, fov=float(z['fov']), isCuda=True)
+    o2e = irb.output2env(K, isCuda=True)
+    env, ax, lw, ww = o2e.output2env(ins[3], ins[4], ins[5])
+    if fused:
+        assert getattr(env, '_irb_sg', None) is not None
+        d, s = rl.forwardEnv(ins[0], ins[1], ins[2], env)
+    else:
+        env_plain = env * 1.0          # drops the SG provenance -> unfused kernels
+        assert getattr(env_plain, '_irb_sg', None) is None
+        d, s = rl.forwardEnv(ins[0], ins[1], ins[2], env_plain)
+    gD = torch.from_numpy(z['gD']).to(dev)
+    gS = torch.from_numpy(z['gS']).to(dev)
+    g = torch.autograd.grad([d, s], ins, [gD, gS])
+    got = dict(env=env, lam_w=lw, wt_w=ww, diff=d, spec=s, g_albedo=g[0], g_normal=g[1], g_rough=g[2], g_axis=g[3],
+               g_lamb=g[4], g_weight=g[5])
+    return {k: v.detach().cpu().numpy() for k, v in got.items()}
+
+
+@pytest.mark.parametrize('path', RENDER, ids=[os.path.basename(p) for p in RENDER])
+@pytest.mark.parametrize('fused', [True, False], ids=['fused', 'unfused'])
+def test_golden_parity(irb, path, fused):
+    z = dict(np.load(path))
+    got = _run(irb, z, fused)
+    report = {}
+    for k, v in got.items():
+        e_ref = relerr(z['ref32_' + k], z['ref64_' + k])
+        e = relerr(v, z['ref64_' + k])
+        report[k] = (e, e_ref)
+        assert e <= max(1e-4, 2 * e_ref), (k, e, e_ref)
+        # and agreement with the reference's own fp32 run
+        assert relerr(v, z['ref32_' + k]) <= 1e-4 + 2 * e_ref, k
+    print(os.path.basename(path), 'fused' if fused else 'unfused',
+          {k: '%.1e/%.1e' % v for k, v in report.items()})
+
+
+def test_oracle_parity_medium(irb):
+    """seeded inputs at a size the oracle finishes in seconds: 2 x (60x80 maps -> 30x40 grid), fp64 oracle"""
+    from oracle import render_oracle as ro
+    B, H, W, R, C, K = 2, 60, 80, 30, 40, 12
+    ins64 = ro.synth_inputs(B, H, W, R, C, K, seed=4321, dtype=torch.float64)
+    for t in ins64:
+        t.requires_grad_(True)
+    g = torch.Generator().manual_seed(7)
+    gD = torch.rand(B, 3, R, C, generator=g)
+    gS = torch.rand(B, 3, R, C, generator=g)
+    d64, s64 = ro.render_sg(*ins64)
+    g64 = torch.autograd.grad((d64 * gD.double()).sum() + (s64 * gS.double()).sum(), ins64)
+    dev = torch.device('cuda')
+    ins = [t.detach().float().to(dev).requires_grad_(True) for t in ins64]
+    rl = irb.renderingLayer(imWidth=C, imHeight=R, isCuda=True)
+    d, s = rl.forwardSG(*ins)
+    gg = torch.autograd.grad([d, s], ins, [gD.to(dev), gS.to(dev)])
+    assert relerr(d.detach().cpu().numpy(), d64.detach().numpy()) <= 1e-4
+    assert relerr(s.detach().cpu().numpy(), s64.detach().numpy()) <= 1e-4
+    for a, b, name in zip(gg, g64, ('albedo', 'normal', 'rough', 'axis', 'lamb', 'weight')):
+        assert relerr(a.cpu().numpy(), b.numpy()) <= 2e-4, name
+
+
+def test_edge_cases_vs_oracle(irb):
+    """degenerate frames and saturated SG parameters: normal || up, zero normal,
+    back-facing normal, |n|>1, lamb = weight = 1 (tan blow-up to 636.6), lamb = 0."""
+    from oracle import render_oracle as ro
+    B, R, C, K = 1, 4, 8, 12
+    ins64 = ro.synth_inputs(B, R, C, R, C, K, seed=99, dtype=torch.float64)
+    alb, nrm, rg, ax, lam, wt = ins64
+    nrm[0, :, 0, 0] = torch.tensor([0.0, 1.0, 0.0])     # parallel to up: camy degenerate
+    nrm[0, :, 0, 1] = torch.tensor([0.0, 0.0, 0.0])     # zero normal: lower clamp
+    nrm[0, :, 0, 2] = torch.tensor([0.0, 0.0, -0.9])    # back-facing
+    nrm[0, :, 0, 3] = torch.tensor([0.3, 0.2, 1.2])     # |n| > 1: upper clamp
+    nrm[0, :, 0, 4] = torch.tensor([0.0, -1.0, 0.0])
+    lam[0, 0] = 1.0
+    wt[0, 0:3] = 1.0
+    lam[0, 1] = 0.0
+    wt[0, 3:6] = 0.0
+    rg[0, 0, 1, :] = -1.0                                # rho = 0 -> alpha2 = 0
+    rg[0, 0, 2, :] = 1.0
+    ins64 = [t.float().double().requires_grad_(True) for t in ins64]
+    g = torch.Generator().manual_seed(8)
+    gD = torch.rand(B, 3, R, C, generator=g)
+    gS = torch.rand(B, 3, R, C, generator=g)
+    d64, s64 = ro.render_sg(*ins64)
+    g64 = torch.autograd.grad((d64 * gD.double()).sum() + (s64 * gS.double()).sum(), ins64)
+    dev = torch.device('cuda')
+    ins = [t.detach().float().to(dev).requires_grad_(True) for t in ins64]
+    rl = irb.renderingLayer(imWidth=C, imHeight=R, isCuda=True)
+    d, s = rl.forwardSG(*ins)
+    gg = torch.autograd.grad([d, s], ins, [gD.to(dev), gS.to(dev)])
+    for t in (d, s) + tuple(gg):
+        assert torch.isfinite(t).all()
+    assert relerr(d.detach().cpu().numpy(), d64.detach().numpy()) <= 1e-4
+    assert relerr(s.detach().cpu().numpy(), s64.detach().numpy()) <= 1e-4
+    for a, b, name in zip(gg, g64, ('albedo', 'normal', 'rough', 'axis', 'lamb', 'weight')):
+        assert relerr(a.cpu().numpy(), b.numpy()) <= 5e-4, name
+
+
+def test_full_size_properties(irb):
+    """BASELINE config 2 size (16 x 240x320, 12 SG) through size-independent properties:
+    linearity in the SG intensities, additivity over lobes, fused == unfused, gradient dot-test."""
+    dev = torch.device('cuda')
+    B, R, C, K = 16, 240, 320, 12
+    g = torch.Generator(device='cuda').manual_seed(1236)
+    alb = torch.rand(B, 3, R, C, device=dev, generator=g)
+    n = torch.randn(B, 3, R, C, device=dev, generator=g)
+    n[:, 2] += 1.5
+    n = n / n.norm(dim=1, keepdim=True) * (0.7 + 0.28 * torch.rand(B, 1, R, C, device=dev, generator=g))
+    rg = torch.rand(B, 1, R, C, device=dev, generator=g) * 2 - 1
+    ax = torch.randn(B, K, 3, R, C, device=dev, generator=g)
+    ax = ax / ax.norm(dim=2, keepdim=True)
+    lam = torch.rand(B, K, R, C, device=dev, generator=g) * 30      # already-warped domain (warp=False)
+    wt = torch.rand(B, 3 * K, R, C, device=dev, generator=g) * 5
+    rl = irb.renderingLayer(imWidth=C, imHeight=R, isCuda=True)
+    d1, s1 = rl.forwardSG(alb, n, rg, ax, lam, wt, warp=False)
+    # linearity in W
+    d2, s2 = rl.forwardSG(alb, n, rg, ax, lam, 2.0 * wt, warp=False)
+    assert relerr((d2).cpu().numpy(), (2 * d1).cpu().numpy()) <= 1e-6
+    assert relerr((s2).cpu().numpy(), (2 * s1).cpu().numpy()) <= 1e-6
+    # additivity over lobes: first 5 + last 7 == all 12
+    o5 = irb.output2env(5, isCuda=True)
+    da, sa = rl.forwardSG(alb, n, rg, ax[:, :5].contiguous(), lam[:, :5].contiguous(), wt[:, :15].contiguous(), warp=False)
+    db, sb = rl.forwardSG(alb, n, rg, ax[:, 5:].contiguous(), lam[:, 5:].contiguous(), wt[:, 15:].contiguous(), warp=False)
+    assert relerr((da + db).cpu().numpy(), d1.cpu().numpy()) <= 2e-6
+    assert relerr((sa + sb).cpu().numpy(), s1.cpu().numpy()) <= 2e-6
+    # fused == unfused on a 4-image slice (env-map 472 MB)
+    o2e = irb.output2env(K, isCuda=True)
+    sl = slice(0, 4)
+    env = o2e.fromSGtoIm(ax[sl].contiguous(), lam[sl].contiguous(), wt[sl].contiguous())
+    du, su = rl.forwardEnv(alb[sl], n[sl], rg[sl], env)
+    assert relerr(du.cpu().numpy(), d1[sl].cpu().numpy()) <= 2e-5
+    assert relerr(su.cpu().numpy(), s1[sl].cpu().numpy()) <= 2e-5
+    # gradient dot-test at full size: <J^T g, dx> == <g, J dx> by central differences along one direction
+    lam_r = torch.rand(B, K, R, C, device=dev, generator=g) * 0.9
+    wt_r = torch.rand(B, 3 * K, R, C, device=dev, generator=g) * 0.9
+    ins = [t.clone().requires_grad_(True) for t in (alb, n, rg, ax, lam_r, wt_r)]
+    d, s = rl.forwardSG(*ins)
+    gD = torch.rand_like(d)
+    gS = torch.rand_like(s)
+    grads = torch.autograd.grad([d, s], ins, [gD, gS])
+    dirs = [torch.randn_like(t) for t in ins]
+    lhs = sum((gi.double() * di.double()).sum() for gi, di in zip(grads, dirs)).item()
+    eps = 1e-3
+    with torch.no_grad():
+        dp, sp = rl.forwardSG(*[t + eps * di for t, di in zip(ins, dirs)])
+        dm, sm = rl.forwardSG(*[t - eps * di for t, di in zip(ins, dirs)])
+    rhs = (((dp - dm).double() * gD.double()).sum() + ((sp - sm).double() * gS.double()).sum()).item() / (2 * eps)
+    assert abs(lhs - rhs) <= 2e-3 * max(abs(lhs), abs(rhs)), (lhs, rhs)
+
+
+def test_k24_and_other_fov(irb):
+    z = dict(np.load(os.path.join(GOLDEN, 'render_ragged_k24.npz')))
+    got = _run(irb, z, True)
+    assert relerr(got['spec'], z['ref64_spec']) <= 1e-4
+
+
+def test_argument_errors(irb):
+    dev = torch.device('cuda')
+    rl = irb.renderingLayer(imWidth=8, imHeight=6, isCuda=True)
+    with pytest.raises(ValueError):
+        rl.forwardEnv(torch.zeros(1, 3, 6, 8, device=dev), torch.zeros(1, 3, 6, 8, device=dev),
+                      torch.zeros(1, 1, 6, 8, device=dev), torch.zeros(1, 3, 6, 8, 4, 16, device=dev))
+    with pytest.raises(ValueError):
+        rl.forwardEnv(torch.zeros(1, 3, 6, 8, device=dev), torch.zeros(1, 3, 6, 8, device=dev),
+                      torch.zeros(1, 1, 6, 8, device=dev), torch.zeros(1, 3, 5, 8, 8, 16, device=dev))
+    o = irb.output2env(12, isCuda=True)
+    with pytest.raises(ValueError):
+        o.output2env(torch.zeros(1, 11, 3, 6, 8, device=dev), torch.zeros(1, 12, 6, 8, device=dev),
+                     torch.zeros(1, 36, 6, 8, device=dev))
+    with pytest.raises(ValueError):
+        o.output2env(torch.zeros(1, 12, 3, 6, 8, device=dev).double(), torch.zeros(1, 12, 6, 8, device=dev),
+                     torch.zeros(1, 36, 6, 8, device=dev))
+
+
+def test_pool_matches_torch(irb):
+    import torch.nn.functional as F
+    from inverserenderingofindoorscene_b200.models import _pool
+    dev = torch.device('cuda')
+    for (H, W, R, C) in ((240, 320, 120, 160), (13, 19, 5, 7), (241, 321, 120, 160), (6, 8, 6, 8), (5, 7, 10, 14)):
+        x = torch.rand(2, 3, H, W, device=dev, requires_grad=True)
+        y = _pool(x, R, C)
+        yr = F.adaptive_avg_pool2d(x, (R, C))
+        assert torch.allclose(y, yr, atol=1e-6)
+        g = torch.rand_like(yr)
+        gx, = torch.autograd.grad(y, x, g)
+        gxr, = torch.autograd.grad(yr, x, g)
+        assert torch.allclose(gx, gxr, atol=1e-6)
