@@ -106,11 +106,12 @@ int irb_avgpool_bwd(const float* g_out, float* g_in, int N, int H, int W, int R,
  * BilateralLayer.BilateralFunction.forward/backward (BilateralLayer.py:24-124).
  *
  * irb_bg_workspace_bytes: size of the opaque grid workspace for B images of H x W.
- * irb_bg_build: guide [B,3,H,W] in [0,1] (multiplied by 255.0f in fp32 as BilateralLayer.py:52
- *   does), builds per image the 5-D XYLUV grid (fp64 coordinates, BilateralGrid.py:44-59),
+ * irb_bg_build: guide [B,3,H,W]; the grid image is fl32(guide * guide_scale) -- pass 255.0f for the
+ *   BilateralLayer call (BilateralLayer.py:52 multiplies the [0,1] guide by 255.0 in float32), 1.0f for an
+ *   image that is already in [0,255]; builds per image the 5-D XYLUV grid (fp64 coordinates, BilateralGrid.py:44-59),
  *   vertex ids = rank of the hash among sorted unique hashes (BilateralGrid.py:61-65),
  *   the +-1 neighbour table (:72-84) and the bistochastisation vectors (:109-120).
- *   nverts_out: HOST int[B], written after an internal stream synchronise (the only sync).
+ *   nverts_out: HOST int[B] or NULL; when given it is written after a stream synchronise (the only sync).
  * irb_bg_vertex_index: copies the per-pixel vertex ids (int32 [B,H*W]) for inspection.
  * irb_bg_solve_fwd: pred [B,ch,H,W], conf [B,1,H,W] -> out [B,ch,H,W];
  *   yhat (fp64, [B, ch, H*W] capacity) receives the bilateral-space solution saved for backward.
@@ -119,7 +120,7 @@ int irb_avgpool_bwd(const float* g_out, float* g_in, int N, int H, int W, int R,
  * BilateralLayer.py:44,79).
  * ------------------------------------------------------------------------------------- */
 size_t irb_bg_workspace_bytes(int B, int H, int W, int ch);
-int irb_bg_build(const float* guide, int B, int H, int W, double sigma_luma, double sigma_chroma,
+int irb_bg_build(const float* guide, float guide_scale, int B, int H, int W, double sigma_luma, double sigma_chroma,
                  double sigma_spatial, void* ws, size_t ws_bytes, int* nverts_out, void* stream);
 int irb_bg_vertex_index(const void* ws, int32_t* idx_out, int B, int H, int W, void* stream);
 int irb_bg_solve_fwd(void* ws, const float* pred, const float* conf, int B, int ch, int H, int W,

@@ -1,22 +1,609 @@
-// irb_bilateral.cu -- bilateral-grid solver (placeholder until the kernels land this round).
+// irb_bilateral.cu -- bilateral-grid solver on the GPU: grid build (hash, sort, unique, neighbour
+// table), bistochastisation, Jacobi-preconditioned CG solve and its adjoint, splat/slice.
+// Replaces BilateralGrid.py:44-207 and the per-image NumPy bridge BilateralLayer.py:24-124.
+//
+// Data layout (all in the caller-owned workspace, per image strided by P = H*W):
+//   idx[P]      vertex of each pixel = rank of its hash among the image's sorted unique hashes
+//   sp[P]       pixels sorted by (hash, pixel)  -> splat is a segmented, ORDERED sum (no atomics;
+//               same summation order as the reference's CSR S.dot(x), hence bit-identical in fp64)
+//   vstart[V+1] segment starts, ukeys[V] sorted unique hashes, nbr[10][P] (+-1 neighbour per dim, -1 = none)
+//   n[P], m[P]  bistochastisation vectors (fp64);  solver vectors x,r,p,q,b (fp64, per channel)
+// Arithmetic is fp64 like the reference (NumPy/SciPy doubles); the vertex indexing is integer-exact.
+// Per-iteration structure of PCG: 2 kernels (p-update + mat-vec + <p,q>;  x/r update + <r,z>, <r,r>),
+// all images and channels batched in each launch, scalars accumulated per (image, channel, iteration).
+#include <stdint.h>
+
 #include "irb_common.cuh"
+
+namespace irb {
+
+constexpr int BG_DIM = 5;
+constexpr int BG_MAX_ITERS = 256;
+constexpr int BG_MAX_CH = 4;
+constexpr int SORT_THREADS = 1024;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+
+struct BgLayout {
+    int B, H, W, ch;
+    size_t P;
+    size_t hdr, idx, vstart, ukeys, nbr, n0, n1, m, m0, keysA, keysB, payA, payB;
+    size_t wsplat, minv, bvec, r, p0, p1, q, sol, scal, total;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static BgLayout make_layout(int B, int H, int W, int ch) {
+    BgLayout L{};
+    L.B = B; L.H = H; L.W = W; L.ch = ch;
+    L.P = (size_t)H * W;
+    const size_t P = L.P, Bz = (size_t)B;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { const size_t r = o; o = align_up(o + bytes); return r; };
+    L.hdr = take(sizeof(int) * Bz);
+    L.idx = take(4 * P * Bz);
+    L.vstart = take(4 * (P + 1) * Bz);
+    L.ukeys = take(8 * P * Bz);
+    L.nbr = take(4 * 2 * BG_DIM * P * Bz);
+    L.n0 = take(8 * P * Bz);
+    L.n1 = take(8 * P * Bz);
+    L.m = take(8 * P * Bz);
+    L.m0 = take(8 * P * Bz);
+    L.keysA = take(8 * P * Bz);
+    L.keysB = take(8 * P * Bz);
+    L.payA = take(4 * P * Bz);
+    L.payB = take(4 * P * Bz);
+    L.wsplat = take(8 * P * Bz);
+    L.minv = take(8 * P * Bz);
+    const size_t vc = 8 * P * Bz * (size_t)(ch > 0 ? ch : 1);
+    L.bvec = take(vc);
+    L.r = take(vc);
+    L.p0 = take(vc);
+    L.p1 = take(vc);
+    L.q = take(vc);
+    L.sol = take(vc);  // adjoint solution (backward)
+    L.scal = take(8 * Bz * BG_MAX_CH * (BG_MAX_ITERS + 2) * 4);
+    L.total = o;
+    return L;
+}
+
+template <typename T> __host__ __device__ inline T* at(void* ws, size_t off) { return reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + off); }
+template <typename T> __host__ __device__ inline const T* at(const void* ws, size_t off) {
+    return reinterpret_cast<const T*>(reinterpret_cast<const char*>(ws) + off);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1. per-pixel hash (BilateralGrid.py:23-24, 44-59, 86-88)
+// ---------------------------------------------------------------------------------------------
+__global__ void bg_keys_kernel(const float* __restrict__ guide, float gscale, void* ws, BgLayout L, double sl, double sc, double ss) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= L.P * L.B) return;
+    const size_t b = t / L.P, p = t % L.P;
+    const int y = (int)(p / L.W), x = (int)(p % L.W);
+    const float* g = guide + b * 3 * L.P + p;
+    // BilateralLayer.py:52: curr_image * 255.0 is a float32 product
+    const double r = (double)__fmul_rn(g[0], gscale), gg = (double)__fmul_rn(g[L.P], gscale),
+                 bl = (double)__fmul_rn(g[2 * L.P], gscale);
+    // np.tensordot -> OpenBLAS dgemm: fma(b, m2, fma(g, m1, r*m0)), then + offset
+    const double Y = fma(bl, 0.114, fma(gg, 0.587, r * 0.299)) + 0.0;
+    const double U = fma(bl, 0.5, fma(gg, -0.331264, r * -0.168736)) + 128.0;
+    const double V = fma(bl, -0.081312, fma(gg, -0.418688, r * 0.5)) + 128.0;
+    // (coord / sigma).astype(int): truncation toward zero of the fp64 quotient
+    const long long cx = (long long)((double)x / ss), cy = (long long)((double)y / ss);
+    const long long cl = (long long)(Y / sl), cu = (long long)(U / sc), cv = (long long)(V / sc);
+    // sum_i coord_i * 255^i  (exact in the reference's fp64 too)
+    const long long key = cx + 255LL * (cy + 255LL * (cl + 255LL * (cu + 255LL * cv)));
+    at<unsigned long long>(ws, L.keysA)[t] = (unsigned long long)key;
+    at<int>(ws, L.payA)[t] = (int)p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2. one CTA per image: stable LSD radix sort of (hash, pixel) on 8-bit digits, then
+//    unique -> vertex ids (np.unique, BilateralGrid.py:64-65)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SORT_THREADS) bg_sort_unique_kernel(void* ws, BgLayout L, int npass) {
+    __shared__ unsigned hist[256 * SORT_WARPS];
+    __shared__ unsigned wtot[SORT_WARPS];
+    __shared__ unsigned carry_s;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t P = L.P;
+    unsigned long long* kA = at<unsigned long long>(ws, L.keysA) + (size_t)b * P;
+    unsigned long long* kB = at<unsigned long long>(ws, L.keysB) + (size_t)b * P;
+    int* pA = at<int>(ws, L.payA) + (size_t)b * P;
+    int* pB = at<int>(ws, L.payB) + (size_t)b * P;
+    const size_t chunk = (P + SORT_WARPS - 1) / SORT_WARPS;
+    const size_t beg = (size_t)warp * chunk, end = beg + chunk < P ? beg + chunk : P;
+    for (int pass = 0; pass < npass; ++pass) {
+        const int shift = 8 * pass;
+        for (int i = tid; i < 256 * SORT_WARPS; i += SORT_THREADS) hist[i] = 0;
+        __syncthreads();
+        // count
+        for (size_t i = beg; i < end; i += 32) {
+            const bool ok = i + lane < end;
+            const unsigned valid = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const unsigned d = (unsigned)(kA[i + lane] >> shift) & 255u;
+                const unsigned peers = __match_any_sync(valid, d);
+                if (lane == __ffs(peers) - 1) hist[d * SORT_WARPS + warp] += __popc(peers);
+            }
+        }
+        __syncthreads();
+        // exclusive scan over (digit major, warp minor): 8192 entries, 8 per thread
+        {
+            unsigned loc[8], s = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                loc[j] = hist[tid * 8 + j];
+                s += loc[j];
+            }
+            unsigned inc = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            if (lane == 31) wtot[warp] = inc;
+            __syncthreads();
+            if (warp == 0) {
+                unsigned v = wtot[lane], iv = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned u = __shfl_up_sync(0xffffffffu, iv, o);
+                    if (lane >= o) iv += u;
+                }
+                wtot[lane] = iv - v;
+            }
+            __syncthreads();
+            unsigned run = wtot[warp] + inc - s;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                hist[tid * 8 + j] = run;
+                run += loc[j];
+            }
+        }
+        __syncthreads();
+        // stable scatter
+        for (size_t i = beg; i < end; i += 32) {
+            const bool ok = i + lane < end;
+            const unsigned valid = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const unsigned long long key = kA[i + lane];
+                const int pay = pA[i + lane];
+                const unsigned d = (unsigned)(key >> shift) & 255u;
+                const unsigned peers = __match_any_sync(valid, d);
+                const unsigned base = hist[d * SORT_WARPS + warp];
+                const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+                __syncwarp(valid);
+                if (lane == __ffs(peers) - 1) hist[d * SORT_WARPS + warp] = base + __popc(peers);
+                kB[base + rank] = key;
+                pB[base + rank] = pay;
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        unsigned long long* tk = kA; kA = kB; kB = tk;
+        int* tp = pA; pA = pB; pB = tp;
+    }
+    // sorted data is now in kA / pA.  unique + rank.
+    int* idx = at<int>(ws, L.idx) + (size_t)b * P;
+    int* vstart = at<int>(ws, L.vstart) + (size_t)b * (P + 1);
+    unsigned long long* ukeys = at<unsigned long long>(ws, L.ukeys) + (size_t)b * P;
+    int* sp = at<int>(ws, L.payB) + (size_t)b * P;  // final sorted pixel list always lands in payB
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (size_t base = 0; base < P; base += SORT_THREADS) {
+        const size_t i = base + tid;
+        const bool ok = i < P;
+        unsigned long long key = 0;
+        int pay = 0;
+        bool head = false;
+        if (ok) {
+            key = kA[i];
+            pay = pA[i];
+            head = (i == 0) || (kA[i - 1] != key);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, head);
+        const unsigned excl_w = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) wtot[warp] = __popc(bal);
+        __syncthreads();
+        unsigned pre = 0, tot = 0;
+        for (int w = 0; w < SORT_WARPS; ++w) {
+            const unsigned c = wtot[w];
+            if (w < warp) pre += c;
+            tot += c;
+        }
+        const unsigned carry = carry_s;
+        if (ok) {
+            const unsigned vid = carry + pre + excl_w + (head ? 1u : 0u) - 1u;
+            if (head) {
+                ukeys[vid] = key;
+                vstart[vid] = (int)i;
+            }
+            idx[pay] = (int)vid;
+            if (pA != sp) sp[i] = pay;
+        }
+        __syncthreads();
+        if (tid == 0) carry_s = carry + tot;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const unsigned V = carry_s;
+        vstart[V] = (int)P;
+        at<int>(ws, L.hdr)[b] = (int)V;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3. neighbour table (BilateralGrid.py:72-84): hash +- 255^d located by binary search
+// ---------------------------------------------------------------------------------------------
+__global__ void bg_nbr_kernel(void* ws, BgLayout L) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t P = L.P;
+    const int b = blockIdx.y;
+    const int V = at<int>(ws, L.hdr)[b];
+    if (t >= (size_t)V) return;
+    const unsigned long long* uk = at<unsigned long long>(ws, L.ukeys) + (size_t)b * P;
+    int* nbr = at<int>(ws, L.nbr) + (size_t)b * 2 * BG_DIM * P;
+    const long long key = (long long)uk[t];
+    long long hv = 1;
+    for (int d = 0; d < BG_DIM; ++d) {
+        for (int s = 0; s < 2; ++s) {
+            const long long target = key + (s ? hv : -hv);
+            int lo = 0, hi = V;  // lower bound
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if ((long long)uk[mid] < target) lo = mid + 1; else hi = mid;
+            }
+            nbr[(size_t)(2 * d + s) * P + t] = (lo < V && (long long)uk[lo] == target) ? lo : -1;
+        }
+        hv *= 255;
+    }
+    // pixel counts m0 = S 1
+    const int* vs = at<int>(ws, L.vstart) + (size_t)b * (P + 1);
+    at<double>(ws, L.m0)[(size_t)b * P + t] = (double)(vs[t + 1] - vs[t]);
+    at<double>(ws, L.n0)[(size_t)b * P + t] = 1.0;
+}
+
+// blur(x)_v = 2*dim*x_v + sum_dims (x[lo] + x[hi])  in the reference's summation order
+// (BilateralGrid.py:96-102: out = 10 x; for each dim: out += B_dim x, B_dim row = [lo, hi] by column)
+__device__ __forceinline__ double bg_blur(const double* __restrict__ x, const int* __restrict__ nbr, size_t P, size_t v) {
+    double out = 2.0 * BG_DIM * x[v];
+#pragma unroll
+    for (int d = 0; d < BG_DIM; ++d) {
+        const int lo = nbr[(size_t)(2 * d) * P + v], hi = nbr[(size_t)(2 * d + 1) * P + v];
+        double t = 0.0;
+        bool any = false;
+        if (lo >= 0) { t = x[lo]; any = true; }
+        if (hi >= 0) { t = any ? t + x[hi] : x[hi]; any = true; }
+        if (any) out += t;
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4. bistochastisation (BilateralGrid.py:109-120)
+// ---------------------------------------------------------------------------------------------
+__global__ void bg_bisto_iter_kernel(void* ws, BgLayout L, int src) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    const size_t P = L.P;
+    if (t >= (size_t)at<int>(ws, L.hdr)[b]) return;
+    const double* n = at<double>(ws, src ? L.n1 : L.n0) + (size_t)b * P;
+    double* nn = at<double>(ws, src ? L.n0 : L.n1) + (size_t)b * P;
+    const int* nbr = at<int>(ws, L.nbr) + (size_t)b * 2 * BG_DIM * P;
+    const double m0 = at<double>(ws, L.m0)[(size_t)b * P + t];
+    nn[t] = sqrt(n[t] * m0 / bg_blur(n, nbr, P, t));
+}
+__global__ void bg_bisto_final_kernel(void* ws, BgLayout L, int src) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    const size_t P = L.P;
+    if (t >= (size_t)at<int>(ws, L.hdr)[b]) return;
+    const double* n = at<double>(ws, src ? L.n1 : L.n0) + (size_t)b * P;
+    const int* nbr = at<int>(ws, L.nbr) + (size_t)b * 2 * BG_DIM * P;
+    at<double>(ws, L.m)[(size_t)b * P + t] = n[t] * bg_blur(n, nbr, P, t);
+    if (src) at<double>(ws, L.n0)[(size_t)b * P + t] = n[t];  // final n always in n0
+}
+
+// ---------------------------------------------------------------------------------------------
+// 5. solver
+// ---------------------------------------------------------------------------------------------
+struct SolveArgs {
+    const float* pred;   // [B,ch,P]  (forward: target; backward: target for grad_conf)
+    const float* conf;   // [B,1,P]
+    const float* rhs;    // forward: pred ; backward: g_out   [B,ch,P]
+    double* x;           // [B,ch,P] solution (yhat buffer of the caller)
+    double lam, dmin, tol;
+    int adjoint;         // 0: b = S(x*w), y0 = b/max(Sw,1e-10) ; 1: b = S(g), y0 = b/S(1)
+};
+
+__device__ __forceinline__ double* scal_ptr(void* ws, const BgLayout& L, int b, int c, int it) {
+    return at<double>(ws, L.scal) + (((size_t)b * BG_MAX_CH + c) * (BG_MAX_ITERS + 2) + it) * 4;
+}
+// slot layout: [it] -> {rho, pq, rr, -};   slot BG_MAX_ITERS+1 -> {bb, -, -, -}
+
+__device__ __forceinline__ void block_atomic_add(double v, double* dst) {
+    // warp shuffle reduction, then one atomic per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(dst, v);
+}
+
+// splat (ordered segmented sums), system diagonal, flat initialisation (BilateralGrid.py:134-145 / 160-168)
+__global__ void bg_setup_kernel(void* ws, BgLayout L, SolveArgs a) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    const size_t P = L.P;
+    const int V = at<int>(ws, L.hdr)[b];
+    const bool ok = t < (size_t)V;
+    double bsum[BG_MAX_CH] = {0, 0, 0, 0};
+    if (ok) {
+        const int* vs = at<int>(ws, L.vstart) + (size_t)b * (P + 1);
+        const int* sp = at<int>(ws, L.payB) + (size_t)b * P;
+        const int s0 = vs[t], s1 = vs[t + 1];
+        double wsum = 0.0;
+        for (int i = s0; i < s1; ++i) {
+            const int p = sp[i];
+            const double w = (double)a.conf[(size_t)b * P + p];
+            wsum += w;
+            for (int c = 0; c < L.ch; ++c) {
+                const double xv = (double)a.rhs[((size_t)b * L.ch + c) * P + p];
+                bsum[c] += a.adjoint ? xv : xv * w;
+            }
+        }
+        const double n = at<double>(ws, L.n0)[(size_t)b * P + t], m = at<double>(ws, L.m)[(size_t)b * P + t];
+        const double diag = a.lam * (m - n * (2.0 * BG_DIM) * n) + wsum;
+        at<double>(ws, L.wsplat)[(size_t)b * P + t] = wsum;
+        at<double>(ws, L.minv)[(size_t)b * P + t] = 1.0 / fmax(diag, a.dmin);
+        const double den = a.adjoint ? at<double>(ws, L.m0)[(size_t)b * P + t] : fmax(wsum, 1e-10);
+        for (int c = 0; c < L.ch; ++c) {
+            at<double>(ws, L.bvec)[((size_t)b * L.ch + c) * P + t] = bsum[c];
+            a.x[((size_t)b * L.ch + c) * P + t] = bsum[c] / den;
+        }
+    }
+    for (int c = 0; c < L.ch; ++c) block_atomic_add(ok ? bsum[c] * bsum[c] : 0.0, scal_ptr(ws, L, b, c, BG_MAX_ITERS + 1));
+}
+
+// A y = lam (m y - n blur(n y)) + wsplat y, with y given by a functor over vertex ids
+template <typename F>
+__device__ __forceinline__ double bg_matvec(F y, const double* __restrict__ n, const int* __restrict__ nbr, size_t P, size_t v,
+                                            double m, double wsp, double lam) {
+    double out = 2.0 * BG_DIM * (n[v] * y(v));
+#pragma unroll
+    for (int d = 0; d < BG_DIM; ++d) {
+        const int lo = nbr[(size_t)(2 * d) * P + v], hi = nbr[(size_t)(2 * d + 1) * P + v];
+        double t = 0.0;
+        bool any = false;
+        if (lo >= 0) { t = n[lo] * y(lo); any = true; }
+        if (hi >= 0) { const double u = n[hi] * y(hi); t = any ? t + u : u; any = true; }
+        if (any) out += t;
+    }
+    const double yv = y(v);
+    return lam * (m * yv - n[v] * out) + wsp * yv;
+}
+
+// r0 = b - A x0 ; rho0 = <r0, M r0> ; rr0 = <r0, r0>
+__global__ void bg_r0_kernel(void* ws, BgLayout L, SolveArgs a) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    const size_t P = L.P;
+    const int V = at<int>(ws, L.hdr)[b];
+    const bool ok = t < (size_t)V;
+    const double* n = at<double>(ws, L.n0) + (size_t)b * P;
+    const int* nbr = at<int>(ws, L.nbr) + (size_t)b * 2 * BG_DIM * P;
+    for (int c = 0; c < L.ch; ++c) {
+        double rho = 0.0, rr = 0.0;
+        if (ok) {
+            const double* x = a.x + ((size_t)b * L.ch + c) * P;
+            const double Ax = bg_matvec([&](size_t j) { return x[j]; }, n, nbr, P, t, at<double>(ws, L.m)[(size_t)b * P + t],
+                                        at<double>(ws, L.wsplat)[(size_t)b * P + t], a.lam);
+            const double r = at<double>(ws, L.bvec)[((size_t)b * L.ch + c) * P + t] - Ax;
+            at<double>(ws, L.r)[((size_t)b * L.ch + c) * P + t] = r;
+            rho = r * at<double>(ws, L.minv)[(size_t)b * P + t] * r;
+            rr = r * r;
+        }
+        double* s = scal_ptr(ws, L, b, c, 0);
+        block_atomic_add(rho, s + 0);
+        block_atomic_add(rr, s + 2);
+    }
+}
+
+__device__ __forceinline__ bool bg_done(void* ws, const BgLayout& L, int b, int c, int it, double tol) {
+    const double* s = scal_ptr(ws, L, b, c, it);
+    const double bb = scal_ptr(ws, L, b, c, BG_MAX_ITERS + 1)[0];
+    // scipy cg: stop when ||r|| < max(atol, rtol*||b||); ||b|| == 0 returns immediately
+    return bb == 0.0 || s[2] < tol * tol * bb || s[0] == 0.0;
+}
+
+// iteration `it`, first half:  p = z + (rho/rho_prev) p ;  q = A p ; pq = <p,q>
+__global__ void bg_pq_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    const size_t P = L.P;
+    const int V = at<int>(ws, L.hdr)[b];
+    const bool ok = t < (size_t)V;
+    const double* n = at<double>(ws, L.n0) + (size_t)b * P;
+    const double* minv = at<double>(ws, L.minv) + (size_t)b * P;
+    const int* nbr = at<int>(ws, L.nbr) + (size_t)b * 2 * BG_DIM * P;
+    for (int c = 0; c < L.ch; ++c) {
+        if (bg_done(ws, L, b, c, it, a.tol)) continue;  // uniform per (image, channel)
+        double pq = 0.0;
+        if (ok) {
+            const double beta = it > 0 ? scal_ptr(ws, L, b, c, it)[0] / scal_ptr(ws, L, b, c, it - 1)[0] : 0.0;
+            const double* r = at<double>(ws, L.r) + ((size_t)b * L.ch + c) * P;
+            const double* pold = at<double>(ws, (it & 1) ? L.p1 : L.p0) + ((size_t)b * L.ch + c) * P;
+            double* pnew = at<double>(ws, (it & 1) ? L.p0 : L.p1) + ((size_t)b * L.ch + c) * P;
+            auto pfun = [&](size_t j) { return it > 0 ? fma(beta, pold[j], minv[j] * r[j]) : minv[j] * r[j]; };
+            const double q = bg_matvec(pfun, n, nbr, P, t, at<double>(ws, L.m)[(size_t)b * P + t],
+                                       at<double>(ws, L.wsplat)[(size_t)b * P + t], a.lam);
+            const double pv = pfun(t);
+            pnew[t] = pv;
+            at<double>(ws, L.q)[((size_t)b * L.ch + c) * P + t] = q;
+            pq = pv * q;
+        }
+        block_atomic_add(pq, scal_ptr(ws, L, b, c, it) + 1);
+    }
+}
+
+// iteration `it`, second half: alpha = rho/pq ; x += alpha p ; r -= alpha q ; next rho, rr
+__global__ void bg_xr_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    const size_t P = L.P;
+    const int V = at<int>(ws, L.hdr)[b];
+    const bool ok = t < (size_t)V;
+    for (int c = 0; c < L.ch; ++c) {
+        if (bg_done(ws, L, b, c, it, a.tol)) continue;
+        double rho = 0.0, rr = 0.0;
+        if (ok) {
+            const double* s = scal_ptr(ws, L, b, c, it);
+            const double alpha = s[0] / s[1];
+            const size_t o = ((size_t)b * L.ch + c) * P + t;
+            const double pv = at<double>(ws, (it & 1) ? L.p0 : L.p1)[o];
+            a.x[o] += alpha * pv;
+            const double r = at<double>(ws, L.r)[o] - alpha * at<double>(ws, L.q)[o];
+            at<double>(ws, L.r)[o] = r;
+            rho = r * at<double>(ws, L.minv)[(size_t)b * P + t] * r;
+            rr = r * r;
+        }
+        double* sn = scal_ptr(ws, L, b, c, it + 1);
+        block_atomic_add(rho, sn + 0);
+        block_atomic_add(rr, sn + 2);
+    }
+}
+
+// slice (BilateralGrid.py:93-94) -> fp32 output
+__global__ void bg_slice_kernel(const void* ws, BgLayout L, const double* __restrict__ x, float* __restrict__ out) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (t >= L.P) return;
+    const int v = at<int>(ws, L.idx)[(size_t)b * L.P + t];
+    for (int c = 0; c < L.ch; ++c) out[((size_t)b * L.ch + c) * L.P + t] = (float)x[((size_t)b * L.ch + c) * L.P + v];
+}
+
+// backward epilogue (BilateralGrid.py:174-183, 203-205)
+__global__ void bg_grad_kernel(const void* ws, BgLayout L, const double* __restrict__ gh, const double* __restrict__ yhat,
+                               const float* __restrict__ pred, const float* __restrict__ conf, float* __restrict__ g_pred,
+                               float* __restrict__ g_conf) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (t >= L.P) return;
+    const int v = at<int>(ws, L.idx)[(size_t)b * L.P + t];
+    const double w = (double)conf[(size_t)b * L.P + t];
+    double gc = 0.0;
+    for (int c = 0; c < L.ch; ++c) {
+        const size_t ov = ((size_t)b * L.ch + c) * L.P + v, op = ((size_t)b * L.ch + c) * L.P + t;
+        const double g = gh[ov];
+        if (g_pred) g_pred[op] = (float)(g * w);
+        gc += -1.0 * (g * yhat[ov]) + g * (double)pred[op];
+    }
+    if (g_conf) g_conf[(size_t)b * L.P + t] = (float)gc;
+}
+
+static int run_pcg(void* ws, const BgLayout& L, SolveArgs a, int maxiter, cudaStream_t st) {
+    const unsigned gx = (unsigned)((L.P + 255) / 256);
+    const dim3 grid(gx, (unsigned)L.B);
+    cudaMemsetAsync(at<double>(ws, L.scal), 0, 8 * (size_t)L.B * BG_MAX_CH * (BG_MAX_ITERS + 2) * 4, st);
+    bg_setup_kernel<<<grid, 256, 0, st>>>(ws, L, a);
+    bg_r0_kernel<<<grid, 256, 0, st>>>(ws, L, a);
+    for (int it = 0; it < maxiter; ++it) {
+        bg_pq_kernel<<<grid, 256, 0, st>>>(ws, L, a, it);
+        bg_xr_kernel<<<grid, 256, 0, st>>>(ws, L, a, it);
+    }
+    return check_launch("bilateral pcg");
+}
+
+}  // namespace irb
+
 using namespace irb;
-extern "C" size_t irb_bg_workspace_bytes(int, int, int, int) { return 0; }
-extern "C" int irb_bg_build(const float*, int, int, int, double, double, double, void*, size_t, int*, void*) {
-    set_error("irb_bg_build: not implemented yet");
-    return IRB_E_UNSUPPORTED;
+
+extern "C" size_t irb_bg_workspace_bytes(int B, int H, int W, int ch) {
+    if (B <= 0 || H <= 0 || W <= 0 || ch <= 0 || ch > BG_MAX_CH) return 0;
+    return make_layout(B, H, W, ch).total;
 }
-extern "C" int irb_bg_vertex_index(const void*, int32_t*, int, int, int, void*) {
-    set_error("irb_bg_vertex_index: not implemented yet");
-    return IRB_E_UNSUPPORTED;
+
+static int bg_check(const void* ws, int B, int H, int W, int ch, const char* who) {
+    IRB_REQUIRE(ws != nullptr, "%s: null workspace", who);
+    IRB_REQUIRE(B > 0 && H > 0 && W > 0, "%s: non-positive shape", who);
+    IRB_REQUIRE(ch > 0 && ch <= BG_MAX_CH, "%s: channels must be 1..%d (got %d)", who, BG_MAX_CH, ch);
+    IRB_REQUIRE(B <= 65535, "%s: B too large", who);
+    IRB_REQUIRE((size_t)H * W < (size_t)1 << 30, "%s: image too large", who);
+    return 0;
 }
-extern "C" int irb_bg_solve_fwd(void*, const float*, const float*, int, int, int, int, double, double, double, int, float*,
-                                double*, void*) {
-    set_error("irb_bg_solve_fwd: not implemented yet");
-    return IRB_E_UNSUPPORTED;
+
+extern "C" int irb_bg_build(const float* guide, float guide_scale, int B, int H, int W, double sigma_luma, double sigma_chroma,
+                            double sigma_spatial, void* ws, size_t ws_bytes, int* nverts_out, void* stream) {
+    if (int rc = bg_check(ws, B, H, W, 1, "bg_build")) return rc;
+    IRB_REQUIRE(guide != nullptr, "bg_build: null guide");
+    IRB_REQUIRE(sigma_luma > 0 && sigma_chroma > 0 && sigma_spatial > 0, "bg_build: sigmas must be positive");
+    // the layout's prefix (everything the build touches) does not depend on ch; ws_bytes is checked for ch=1
+    const BgLayout L = make_layout(B, H, W, 1);
+    if (ws_bytes < L.total) {
+        set_error("bg_build: workspace too small (%zu < %zu)", ws_bytes, L.total);
+        return IRB_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t tot = L.P * (size_t)B;
+    bg_keys_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(guide, guide_scale, ws, L, sigma_luma, sigma_chroma, sigma_spatial);
+    // hash < 255^5 < 2^40 whenever every coordinate is < 255 (the reference's own requirement); otherwise
+    // sort all 64 bits so that aliasing hashes are still ordered exactly like np.unique orders them
+    const double maxc = fmax(fmax((double)W / sigma_spatial, (double)H / sigma_spatial), fmax(256.0 / sigma_luma, 384.0 / sigma_chroma));
+    const int npass = maxc < 254.0 ? 5 : 7;  // odd: the sorted result must land in keysB / payB
+    bg_sort_unique_kernel<<<B, SORT_THREADS, 0, st>>>(ws, L, npass);
+    const dim3 grid((unsigned)((L.P + 255) / 256), (unsigned)B);
+    bg_nbr_kernel<<<grid, 256, 0, st>>>(ws, L);
+    for (int i = 0; i < 10; ++i) bg_bisto_iter_kernel<<<grid, 256, 0, st>>>(ws, L, i & 1);
+    bg_bisto_final_kernel<<<grid, 256, 0, st>>>(ws, L, 0);  // after 10 iterations n is back in n0
+    if (int rc = check_launch("bg_build")) return rc;
+    if (nverts_out) {
+        cudaError_t e = cudaMemcpyAsync(nverts_out, at<int>(ws, L.hdr), sizeof(int) * B, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            set_error("bg_build: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+    }
+    return 0;
 }
-extern "C" int irb_bg_solve_bwd(void*, const float*, const float*, const float*, const double*, int, int, int, int, double,
-                                double, double, int, float*, float*, void*) {
-    set_error("irb_bg_solve_bwd: not implemented yet");
-    return IRB_E_UNSUPPORTED;
+
+extern "C" int irb_bg_vertex_index(const void* ws, int32_t* idx_out, int B, int H, int W, void* stream) {
+    if (int rc = bg_check(ws, B, H, W, 1, "bg_vertex_index")) return rc;
+    IRB_REQUIRE(idx_out != nullptr, "bg_vertex_index: null output");
+    const BgLayout L = make_layout(B, H, W, 1);
+    const cudaError_t e = cudaMemcpyAsync(idx_out, at<int>(ws, L.idx), 4 * L.P * (size_t)B, cudaMemcpyDeviceToDevice,
+                                          (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        set_error("bg_vertex_index: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+extern "C" int irb_bg_solve_fwd(void* ws, const float* pred, const float* conf, int B, int ch, int H, int W, double lam,
+                                double A_diag_min, double cg_tol, int cg_maxiter, float* out, double* yhat, void* stream) {
+    if (int rc = bg_check(ws, B, H, W, ch, "bg_solve_fwd")) return rc;
+    IRB_REQUIRE(pred && conf && out && yhat, "bg_solve_fwd: null pointer");
+    IRB_REQUIRE(cg_maxiter >= 0 && cg_maxiter <= BG_MAX_ITERS, "bg_solve_fwd: cg_maxiter must be in [0,%d]", BG_MAX_ITERS);
+    const BgLayout L = make_layout(B, H, W, ch);
+    cudaStream_t st = (cudaStream_t)stream;
+    SolveArgs a{pred, conf, pred, yhat, lam, A_diag_min, cg_tol, 0};
+    if (int rc = run_pcg(ws, L, a, cg_maxiter, st)) return rc;
+    const dim3 grid((unsigned)((L.P + 255) / 256), (unsigned)B);
+    bg_slice_kernel<<<grid, 256, 0, st>>>(ws, L, yhat, out);
+    return check_launch("bg_solve_fwd");
+}
+
+extern "C" int irb_bg_solve_bwd(void* ws, const float* pred, const float* conf, const float* g_out, const double* yhat,
+                                int B, int ch, int H, int W, double lam, double A_diag_min, double cg_tol, int cg_maxiter,
+                                float* g_pred, float* g_conf, void* stream) {
+    if (int rc = bg_check(ws, B, H, W, ch, "bg_solve_bwd")) return rc;
+    IRB_REQUIRE(pred && conf && g_out && yhat, "bg_solve_bwd: null pointer");
+    IRB_REQUIRE(cg_maxiter >= 0 && cg_maxiter <= BG_MAX_ITERS, "bg_solve_bwd: cg_maxiter must be in [0,%d]", BG_MAX_ITERS);
+    const BgLayout L = make_layout(B, H, W, ch);
+    cudaStream_t st = (cudaStream_t)stream;
+    double* gh = at<double>(ws, L.sol);
+    SolveArgs a{pred, conf, g_out, gh, lam, A_diag_min, cg_tol, 1};
+    if (int rc = run_pcg(ws, L, a, cg_maxiter, st)) return rc;
+    const dim3 grid((unsigned)((L.P + 255) / 256), (unsigned)B);
+    bg_grad_kernel<<<grid, 256, 0, st>>>(ws, L, gh, yhat, pred, conf, g_pred, g_conf);
+    return check_launch("bg_solve_bwd");
 }

@@ -1,0 +1,128 @@
+"""GPU parity tests of the bilateral solver through the public API (BilateralLayer.BilateralFunction ->
+ctypes -> irb_bg_* -> sm_100a kernels): vertex indexing bit-exact against the reference-generated
+fixtures and the oracle, solver outputs / gradients within 1e-4 (inf-norm normalised)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, relerr
+
+pytestmark = pytest.mark.gpu
+BILAT = sorted(glob.glob(os.path.join(GOLDEN, 'bilateral_*.npz')))
+
+
+@pytest.fixture(scope='module')
+def mods():
+    from inverserenderingofindoorscene_b200 import BilateralLayer, BilateralGrid, _lib
+    _lib.lib()
+    assert torch.cuda.is_available()
+    return BilateralLayer, BilateralGrid
+
+
+def _apply(BL, guide, pred, conf, gout, sig, bsp):
+    dev = torch.device('cuda')
+    g = torch.from_numpy(guide).to(dev)
+    p = torch.from_numpy(pred).to(dev).requires_grad_(True)
+    c = torch.from_numpy(conf).to(dev).requires_grad_(True)
+    gp = torch.tensor(sig, dtype=torch.float32, device=dev)
+    bp = torch.tensor(bsp, dtype=torch.float32, device=dev)
+    out, c2 = BL.BilateralFunction.apply(g, p, c, gp, bp)
+    gpred, gconf = torch.autograd.grad(out, [p, c], torch.from_numpy(gout).to(dev))
+    return out.detach().cpu().numpy(), gpred.cpu().numpy(), gconf.cpu().numpy()
+
+
+@pytest.mark.parametrize('path', BILAT, ids=[os.path.basename(p) for p in BILAT])
+def test_golden_parity(mods, path):
+    BL, BG = mods
+    z = dict(np.load(path))
+    guide, pred, conf, gout = z['guide'], z['pred'], z['conf'], z['gout']
+    sig = [float(x) for x in z['sig']]
+    bsp = [float(x) for x in z['bsp']]
+    B, ch, H, W = pred.shape
+    out, gpred, gconf = _apply(BL, guide, pred, conf, gout, sig, bsp)
+    for i in range(B):
+        # bit-exact vertex assignment (BilateralGrid.py:44-65) through the NumPy facade
+        grid = BG.BilateralGrid(np.transpose(guide[i], (1, 2, 0)) * np.float32(255.0), sigma_luma=sig[0],
+                                sigma_chroma=sig[1], sigma_spatial=sig[2])
+        assert grid.nvertices == int(z['nverts%d' % i])
+        assert np.array_equal(grid.idx, z['idx%d' % i])
+        assert relerr(np.transpose(out[i], (1, 2, 0)), z['xhat%d' % i]) <= 1e-4
+        assert relerr(np.transpose(gpred[i], (1, 2, 0)), z['g_pred%d' % i]) <= 1e-4
+        assert relerr(gconf[i, 0], z['g_conf%d' % i]) <= 1e-4
+        # facade solve: yhat in bilateral space
+        params = {'lam': bsp[0], 'A_diag_min': bsp[1], 'cg_tol': bsp[2], 'cg_maxiter': int(bsp[3])}
+        xhat, yhat = BG.solve(grid, np.transpose(pred[i], (1, 2, 0)), conf[i, 0], params, (H, W, ch))
+        assert relerr(yhat, z['yhat%d' % i]) <= 1e-6
+        gt, gc = BG.solveForGrad(grid, np.transpose(gout[i], (1, 2, 0)), conf[i, 0], params, (H, W, ch), yhat,
+                                 np.transpose(pred[i], (1, 2, 0)))
+        assert relerr(gt, z['g_pred%d' % i]) <= 1e-4 and relerr(gc, z['g_conf%d' % i]) <= 1e-4
+
+
+@pytest.mark.parametrize('mode,ch', [(0, 3), (2, 1), (4, 1)])
+def test_oracle_parity_medium(mods, mode, ch):
+    """240x320 smooth guide, presets of BilateralLayer.py:131-189, against the CPU oracle."""
+    from oracle import bilateral_oracle as bo
+    BL, BG = mods
+    sig, bsp = BL._PRESETS[mode]
+    B, H, W = 2, 240, 320
+    guide = bo.synth_guide(B, H, W, blur_sigma=8.0, seed=1238 + mode)
+    rng = np.random.default_rng(mode)
+    pred = rng.random((B, ch, H, W)).astype(np.float32)
+    conf = (0.05 + 0.95 * rng.random((B, 1, H, W))).astype(np.float32)
+    gout = rng.standard_normal((B, ch, H, W)).astype(np.float32)
+    o_out, yhats, grids = bo.bilateral_forward(guide, pred, conf, sig, (bsp[0], bsp[1], bsp[2], int(bsp[3])))
+    o_gp, o_gc = bo.bilateral_backward(guide, pred, conf, gout, yhats, sig, (bsp[0], bsp[1], bsp[2], int(bsp[3])))
+    out, gpred, gconf = _apply(BL, guide, pred, conf, gout, list(sig), list(bsp))
+    for i in range(B):
+        grid = BG.BilateralGrid(np.transpose(guide[i], (1, 2, 0)) * np.float32(255.0), sigma_luma=sig[0],
+                                sigma_chroma=sig[1], sigma_spatial=sig[2])
+        assert grid.nvertices == grids[i].nvertices
+        assert np.array_equal(grid.idx, grids[i].idx)
+    assert relerr(out, o_out) <= 1e-4
+    assert relerr(gpred, o_gp) <= 1e-4
+    assert relerr(gconf, o_gc) <= 1e-4
+
+
+def test_full_size_properties(mods):
+    """BASELINE config 4 size (8 x 480x640, mode 0) through size-independent properties:
+    constants are reproduced (A_smooth 1 = 0), linearity in the target, vertex count sanity."""
+    from oracle import bilateral_oracle as bo
+    BL, BG = mods
+    dev = torch.device('cuda')
+    B, H, W, ch = 8, 480, 640, 3
+    guide = torch.from_numpy(bo.synth_guide(B, H, W, blur_sigma=8.0, seed=1238)).to(dev)
+    conf = 0.05 + 0.95 * torch.rand(B, 1, H, W, device=dev)
+    gp = torch.tensor([8., 2., 7.], device=dev)
+    bp = torch.tensor([200., 1e-5, 1e-5, 12.], device=dev)
+    const = torch.full((B, ch, H, W), 0.37, device=dev)
+    out, _ = BL.BilateralFunction.apply(guide, const, conf, gp, bp)
+    assert float((out - 0.37).abs().max()) <= 1e-5
+    p1 = torch.rand(B, ch, H, W, device=dev)
+    p2 = torch.rand(B, ch, H, W, device=dev)
+    o1, _ = BL.BilateralFunction.apply(guide, p1, conf, gp, bp)
+    o2, _ = BL.BilateralFunction.apply(guide, p2, conf, gp, bp)
+    o12, _ = BL.BilateralFunction.apply(guide, p1 + 2 * p2, conf, gp, bp)
+    assert relerr((o1 + 2 * o2).cpu().numpy(), o12.cpu().numpy()) <= 1e-5
+    # smoothing: output range within input range
+    assert float(o1.min()) >= -1e-3 and float(o1.max()) <= 1 + 1e-3
+
+
+def test_layer_module(mods):
+    BL, BG = mods
+    dev = torch.device('cuda')
+    torch.manual_seed(0)
+    layer = BL.BilateralLayer(mode=0).to(dev)
+    assert sorted(k.split('.')[0] for k in layer.state_dict()) == sorted(
+        ['conv1'] * 2 + ['gn1'] * 2 + ['conv2'] * 2 + ['gn2'] * 2 + ['dconv1'] * 2 + ['dgn1'] * 2 + ['dconv2'] * 2 +
+        ['dgn2'] * 2 + ['dconvFinal'] * 2)
+    im = torch.rand(2, 3, 64, 96, device=dev)
+    feat = torch.rand(2, 3, 64, 96, device=dev)
+    pred = torch.rand(2, 3, 64, 96, device=dev, requires_grad=True)
+    out, conf = layer(im, feat, pred)
+    assert tuple(out.shape) == (2, 3, 64, 96) and tuple(conf.shape) == (2, 1, 64, 96)
+    (out.sum()).backward()
+    assert pred.grad is not None and torch.isfinite(pred.grad).all()
+    assert layer.dconvFinal.weight.grad is not None and torch.isfinite(layer.dconvFinal.weight.grad).all()

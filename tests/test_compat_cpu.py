@@ -1,0 +1,30 @@
+import types
+
+from inverserenderingofindoorscene_b200 import BilateralLayer, compat, models
+
+
+def test_patch_and_unpatch():
+    ref_m = types.ModuleType('models')
+    ref_b = types.ModuleType('BilateralLayer')
+    sentinel = object()
+    ref_m.renderingLayer = sentinel
+    ref_m.encoder0 = sentinel
+    compat.patch_reference(ref_m, ref_b)
+    assert ref_m.renderingLayer is models.renderingLayer and ref_m.output2env is models.output2env
+    assert ref_m.LSregressDiffSpec is models.LSregressDiffSpec and ref_m.encoder0 is sentinel
+    assert ref_b.BilateralFunction is BilateralLayer.BilateralFunction
+    assert ref_b.BilateralLayer is BilateralLayer.BilateralLayer
+    compat.unpatch()
+    assert ref_m.renderingLayer is sentinel
+
+
+def test_bilateral_layer_shell_cpu():
+    import torch
+    layer = BilateralLayer.BilateralLayer(mode=2, isCuda=False)
+    keys = sorted(set(k.split('.')[0] for k in layer.state_dict()))
+    assert keys == sorted(['conv1', 'gn1', 'conv2', 'gn2', 'dconv1', 'dgn1', 'dconv2', 'dgn2', 'dconvFinal'])
+    assert sum(p.numel() for p in layer.parameters()) > 10000
+    assert layer.conv1.in_channels == 4
+    assert [round(float(x), 6) for x in layer.grid_params_arr] == [8, 2, 8]
+    assert [float(x) for x in layer.bs_params_arr][0] == 300 and int(layer.bs_params_arr[3]) == 10
+    assert layer.computePadding(5, 8) == [2, 1] and layer.computePadding(4, 8) == [2, 2]
