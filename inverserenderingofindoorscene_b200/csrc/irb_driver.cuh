@@ -41,17 +41,27 @@ IRB_HD void load_lobes(Lobes<T, KC>& L, const RenderSgArgs& a, size_t b, size_t 
         const int kk = k0 + k;
         if (kk < a.K) {
             const size_t oa = ((b * a.K + kk) * 3) * plane + pix;
-            L.ax[k] = (T)a.axis[oa];
-            L.ay[k] = (T)a.axis[oa + plane];
-            L.az[k] = (T)a.axis[oa + 2 * plane];
             T lam = (T)a.lamb[(b * a.K + kk) * plane + pix];
             if (a.warp) lam = sg_warp<T>(lam);
-            L.lam[k] = lam * Consts<T>::LOG2E;
+            lam *= Consts<T>::LOG2E;
+            L.lam[k] = lam;
+            L.bx[k] = lam * (T)a.axis[oa];
+            L.by[k] = lam * (T)a.axis[oa + plane];
+            L.bz[k] = lam * (T)a.axis[oa + 2 * plane];
         } else {  // padding lobe: contributes exactly zero (its weight is taken as 0)
-            L.ax[k] = L.ay[k] = L.az[k] = T(0);
+            L.bx[k] = L.by[k] = L.bz[k] = T(0);
             L.lam[k] = T(0);
         }
     }
+}
+
+// dL/dlam_k = sum_d T (a.w_d - 1) = S / lam'   (S = sum_d T arg, arg = lam' (a.w_d - 1)).
+// lam' == 0 (lambOrig == 0 exactly, a value the LightNet head can emit): e == 1 and
+// sum_d T (a.w_d - 1) = a.M - N with N = sum_d T = P U + Q V.
+template <typename T>
+IRB_HD T lobe_lam_grad(T S, T lam, T mx, T my, T mz, T N, const float* axis, size_t oa, size_t plane) {
+    if (lam != T(0)) return S / lam;
+    return (T)axis[oa] * mx + (T)axis[oa + plane] * my + (T)axis[oa + 2 * plane] * mz - N;
 }
 
 template <typename T> IRB_HD T load_weight(const RenderSgArgs& a, size_t b, size_t pix, size_t plane, int kk, int c) {
@@ -126,21 +136,23 @@ IRB_HD void load_PQ(T (&P)[KC], T (&Q)[KC], const RenderSgArgs& a, size_t b, siz
 }
 
 template <typename T, int KC>
-IRB_HD void store_lobe_grads(const LobeGrads<T, KC>& lg, const Lobes<T, KC>& L, const RenderSgArgs& a, size_t b, size_t pix,
-                             size_t plane, int k0, const T (&gDa)[3], const T (&gS)[3], T (&gAlb)[3]) {
+IRB_HD void store_lobe_grads(const LobeGrads<T, KC>& lg, const Lobes<T, KC>& L, const T (&P)[KC], const T (&Q)[KC],
+                             const RenderSgArgs& a, size_t b, size_t pix, size_t plane, int k0, const T (&gDa)[3],
+                             const T (&gS)[3], T (&gAlb)[3]) {
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
         const int kk = k0 + k;
         if (kk < a.K) {
             const T lam = L.lam[k] * Consts<T>::LN2;  // undo the log2e fold
+            const size_t oa = ((b * a.K + kk) * 3) * plane + pix;
             if (a.g_axis) {
-                const size_t oa = ((b * a.K + kk) * 3) * plane + pix;
                 a.g_axis[oa] = (float)(lam * lg.mx[k]);
                 a.g_axis[oa + plane] = (float)(lam * lg.my[k]);
                 a.g_axis[oa + 2 * plane] = (float)(lam * lg.mz[k]);
             }
             if (a.g_lamb) {
-                T g = lg.gl[k];
+                T g = lobe_lam_grad<T>(lg.S[k], L.lam[k], lg.mx[k], lg.my[k], lg.mz[k], P[k] * lg.U[k] + Q[k] * lg.V[k],
+                                       a.axis, oa, plane);
                 if (a.warp) g *= sg_warp_grad<T>(lam);
                 a.g_lamb[(b * a.K + kk) * plane + pix] = (float)g;
             }
@@ -184,7 +196,7 @@ IRB_HD void drv_render_sg_bwd(const RenderSgArgs& a, const EnvTab& tab, size_t b
         load_PQ<T, KP>(P, Q, a, b, pix, plane, 0, gDa, gS);
         LobeGrads<T, KP> lg;
         sweep_bwd<T, KP, PIX, LOBE>(px, L, P, Q, tab, pg, lg);
-        if (LOBE) store_lobe_grads<T, KP>(lg, L, a, b, pix, plane, 0, gDa, gS, gAlb);
+        if (LOBE) store_lobe_grads<T, KP>(lg, L, P, Q, a, b, pix, plane, 0, gDa, gS, gAlb);
     } else {
         if (PIX) {
             Lobes<T, KP> L;
@@ -202,7 +214,7 @@ IRB_HD void drv_render_sg_bwd(const RenderSgArgs& a, const EnvTab& tab, size_t b
                 load_PQ<T, KL>(P, Q, a, b, pix, plane, k0, gDa, gS);
                 LobeGrads<T, KL> lg;
                 sweep_bwd<T, KL, false, true>(px, L, P, Q, tab, pg, lg);
-                store_lobe_grads<T, KL>(lg, L, a, b, pix, plane, k0, gDa, gS, gAlb);
+                store_lobe_grads<T, KL>(lg, L, P, Q, a, b, pix, plane, k0, gDa, gS, gAlb);
             }
         }
     }

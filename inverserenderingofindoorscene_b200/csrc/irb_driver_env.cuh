@@ -88,7 +88,7 @@ template <typename T, int KC> IRB_HD void drv_sg_to_env_fwd(const SgEnvArgs& s, 
                 E[0][u] = E[1][u] = E[2][u] = T(0);
 #pragma unroll
                 for (int k = 0; k < KC; ++k) {
-                    const T e = x_exp2(L.lam[k] * lobe_dm1(L.ax[k], L.ay[k], L.az[k], wx, wy, wz));
+                    const T e = x_exp2(lobe_arg(L.bx[k], L.by[k], L.bz[k], L.lam[k], wx, wy, wz));
                     E[0][u] += W[k][0] * e;
                     E[1][u] += W[k][1] * e;
                     E[2][u] += W[k][2] * e;
@@ -117,10 +117,10 @@ template <typename T, int KC> IRB_HD void drv_sg_to_env_bwd(const SgEnvArgs& s, 
     for (int k0 = 0; k0 < s.K; k0 += KC) {
         Lobes<T, KC> L;
         load_lobes(L, a, b, pix, plane, k0);
-        T W[KC][3], gW[KC][3], gl[KC], mx[KC], my[KC], mz[KC];
+        T W[KC][3], gW[KC][3], gl[KC], nn[KC], mx[KC], my[KC], mz[KC];
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
-            gl[k] = mx[k] = my[k] = mz[k] = T(0);
+            gl[k] = nn[k] = mx[k] = my[k] = mz[k] = T(0);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 W[k][c] = (k0 + k < s.K) ? load_weight<T>(a, b, pix, plane, k0 + k, c) : T(0);
@@ -139,13 +139,14 @@ template <typename T, int KC> IRB_HD void drv_sg_to_env_bwd(const SgEnvArgs& s, 
                 const T wx = (T)tab.lx[d0 + u], wy = (T)tab.ly[d0 + u], wz = (T)tab.lz[d0 + u];
 #pragma unroll
                 for (int k = 0; k < KC; ++k) {
-                    const T dm1 = lobe_dm1(L.ax[k], L.ay[k], L.az[k], wx, wy, wz);
-                    const T e = x_exp2(L.lam[k] * dm1);
+                    const T arg = lobe_arg(L.bx[k], L.by[k], L.bz[k], L.lam[k], wx, wy, wz);
+                    const T e = x_exp2(arg);
                     gW[k][0] += G[0][u] * e;
                     gW[k][1] += G[1][u] * e;
                     gW[k][2] += G[2][u] * e;
                     const T t = e * (G[0][u] * W[k][0] + G[1][u] * W[k][1] + G[2][u] * W[k][2]);
-                    gl[k] += t * dm1;
+                    gl[k] += t * arg;
+                    nn[k] += t;
                     mx[k] += t * wx;
                     my[k] += t * wy;
                     mz[k] += t * wz;
@@ -157,14 +158,14 @@ template <typename T, int KC> IRB_HD void drv_sg_to_env_bwd(const SgEnvArgs& s, 
             const int kk = k0 + k;
             if (kk < s.K) {
                 const T lam = L.lam[k] * Consts<T>::LN2;
+                const size_t oa = ((b * s.K + kk) * 3) * plane + pix;
                 if (s.g_axis) {
-                    const size_t oa = ((b * s.K + kk) * 3) * plane + pix;
                     s.g_axis[oa] = (float)(lam * mx[k]);
                     s.g_axis[oa + plane] = (float)(lam * my[k]);
                     s.g_axis[oa + 2 * plane] = (float)(lam * mz[k]);
                 }
                 if (s.g_lamb) {
-                    T g = gl[k];
+                    T g = lobe_lam_grad<T>(gl[k], L.lam[k], mx[k], my[k], mz[k], nn[k], s.axis, oa, plane);
                     if (s.warp) g *= sg_warp_grad<T>(lam);
                     s.g_lamb[(b * s.K + kk) * plane + pix] = (float)g;
                 }

@@ -47,7 +47,9 @@ IRB_HD float x_exp2(float x) {
 IRB_HD double x_exp2(double x) { return exp2(x); }
 IRB_HD float x_rsqrt(float x) {
 #if defined(__CUDA_ARCH__)
-    return rsqrtf(x);
+    float y;  // arguments are clamped away from zero by the callers: no denormal guard needed
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 #else
     return 1.0f / sqrtf(x);
 #endif
@@ -57,7 +59,9 @@ IRB_HD float x_sqrt(float x) { return sqrtf(x); }
 IRB_HD double x_sqrt(double x) { return sqrt(x); }
 IRB_HD float x_rcp(float x) {
 #if defined(__CUDA_ARCH__)
-    return __frcp_rn(x);
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 #else
     return 1.0f / x;
 #endif
@@ -106,20 +110,30 @@ template <typename T> IRB_HD V3<T> scale(T a, const V3<T>& x) { return V3<T>{a *
 // exact value for fp32 inputs (the fp64 oracle's value).
 template <typename T> IRB_HD T sg_warp(T x);
 template <> IRB_HD double sg_warp<double>(double x) { return tan(Consts<double>::PI / 2 * (0.999 * x)); }
+// tan(z) on [0, pi/4]: z * Q(z^2), Q fitted for minimum relative error (1.3e-7 evaluated in fp32)
+IRB_HD float tan_q(float z) {
+    const float u = z * z;
+    float q = 0.009265977889299393f;
+    q = fmaf(q, u, 0.0033387888688594103f);
+    q = fmaf(q, u, 0.02428046613931656f);
+    q = fmaf(q, u, 0.053457971662282944f);
+    q = fmaf(q, u, 0.13338157534599304f);
+    q = fmaf(q, u, 0.3333318531513214f);
+    q = fmaf(q, u, 1.0f);
+    return z * q;
+}
 template <> IRB_HD float sg_warp<float>(float x) {
     const float c_hi = 0.999f;                                   // fl(0.999)
     const float c_lo = (float)(0.999 - (double)0.999f);          // residual
+    const float HALF_PI = 1.57079632679489661923f;
+    // lower half: tan(pi/2 * 0.999 x) directly; upper half: cot(pi/2 * (1 - 0.999 x)) -- both arguments
+    // stay in [0, pi/4] where the condition number of tan is <= pi/2.
+    const float a = fmaf(c_lo, x, c_hi * x);                     // 0.999 x
     float t = fmaf(-c_hi, x, 1.0f);
-    t = fmaf(-c_lo, x, t);                                       // t = 1 - 0.999 x  (x in [0,1])
-    const float y = 1.57079632679489661923f * t;                 // in (0.0015, pi/2]
-    float s, c;
-#if defined(__CUDA_ARCH__)
-    sincosf(y, &s, &c);
-#else
-    s = sinf(y);
-    c = cosf(y);
-#endif
-    return c / s;
+    t = fmaf(-c_lo, x, t);                                       // 1 - 0.999 x, single rounding of the exact value
+    const bool low = a <= 0.5f;
+    const float tz = tan_q(HALF_PI * (low ? a : t));
+    return low ? tz : 1.0f / tz;
 }
 // d tan(c x)/dx = c (1 + tan^2)
 template <typename T> IRB_HD T sg_warp_grad(T y) {
@@ -133,6 +147,7 @@ template <typename T> struct Pixel {
     T nn_dev;                 // |n|^2 - 1 in exact arithmetic (0 unless the s clamp is active)
     T un, pn, qn;             // up.n, clamped |p|, clamped |q|
     bool p_ok, q_ok;          // norms above F.normalize eps
+    bool regular;             // unit normal, well-conditioned orthonormal frame: local-frame fast path is exact
     T rho, k, alpha2, ndv_raw, ndv, n1, F0;
 };
 
@@ -175,6 +190,7 @@ IRB_HD void pixel_setup(Pixel<T>& px, const V3<T>& nt, T rough, const V3<T>& v, 
     px.ndv_raw = dot(px.n, v);
     px.ndv = x_clamp(px.ndv_raw, T(0), T(1));
     px.n1 = px.ndv * (T(1) - px.k) + px.k;
+    px.regular = (px.s >= (T)1e-6) && (px.s <= T(1)) && (pl >= (T)1e-2) && px.q_ok;
 }
 
 // per-direction forward quantities (kept for the backward of the same direction)
@@ -315,6 +331,114 @@ IRB_HD void pixel_bwd_finish(const PixelGrad<T>& g, const Pixel<T>& px, const V3
     (void)nt;
     const T g_rho = g.g_alpha2 * T(4) * px.rho * px.rho * px.rho + g_k * (px.rho + T(1)) * T(0.25);
     g_rough = g_rho * T(0.5);
+}
+
+
+// =============================================================================================
+// Regular-regime fast path.  When 1e-6 <= |n~|^2 <= 1 (every real caller: normals are pooled
+// means of unit vectors) the frame (camx, camy, n) is orthonormal, so the shading of
+// models.py:482-509 can be evaluated in the pixel's LOCAL frame where n = (0,0,1), l = ls[d]
+// and n.l = ls[d].z is a constant: no world-space l/h vectors, 1 - ndh^2 = (Mx^2+My^2)/|M|^2
+// without cancellation, and d(n.l)/d(normal) = 0 so that whole gradient branch disappears
+// (SURVEY.md 8a "derived identities").  ~22 FMA-pipe ops + 3 SFU ops per direction forward,
+// ~45 backward, against ~70 / ~190 for the general path, which remains the fallback for
+// clamped / degenerate pixels and is what the reference's autograd does there.
+// =============================================================================================
+template <typename T> struct PixelLocal {
+    T vx, vy, vz;  // view vector in the (camx, camy, n) frame
+};
+template <typename T> IRB_HD void pixel_local_setup(PixelLocal<T>& pl, const Pixel<T>& px) {
+    pl.vx = dot(px.v, px.camx);
+    pl.vy = dot(px.v, px.camy);
+    pl.vz = dot(px.v, px.n);
+}
+
+template <typename T> struct DirL {
+    T Mx, My, Mz, rinv, vdh, p2, F, ndh_raw, ndh, n0, n2, nom_raw, inv_nom, spec;
+    bool mm_ok;
+};
+
+template <typename T> IRB_HD void dir_fwd_local(DirL<T>& dr, const Pixel<T>& px, const PixelLocal<T>& pl, T wx, T wy, T wz) {
+    dr.Mx = pl.vx + wx;
+    dr.My = pl.vy + wy;
+    dr.Mz = pl.vz + wz;                       // M = v + l = 2 m
+    const T q = dr.Mx * dr.Mx + dr.My * dr.My;
+    const T MM = q + dr.Mz * dr.Mz;           // 4 m.m
+    dr.mm_ok = MM >= (T)4e-6;                 // clamp(m.m, min=1e-6), models.py:487
+    dr.rinv = x_rsqrt(x_max(MM, (T)4e-6));    // h = M * rinv
+    dr.vdh = (pl.vx * dr.Mx + pl.vy * dr.My + pl.vz * dr.Mz) * dr.rinv;
+    dr.p2 = x_exp2((T(-5.55472) * dr.vdh - T(6.98316)) * dr.vdh);
+    dr.F = px.F0 + (T(1) - px.F0) * dr.p2;
+    dr.ndh_raw = dr.Mz * dr.rinv;
+    dr.ndh = x_clamp(dr.ndh_raw, T(0), T(1));
+    if (dr.ndh_raw <= T(0)) {
+        dr.n0 = T(1);
+    } else if (dr.ndh_raw >= T(1)) {
+        dr.n0 = px.alpha2;
+    } else if (dr.mm_ok) {
+        dr.n0 = q * dr.rinv * dr.rinv + px.alpha2 * dr.ndh * dr.ndh;   // 1 - ndh^2 = (Mx^2+My^2)/|M|^2
+    } else {
+        dr.n0 = dr.ndh * dr.ndh * (px.alpha2 - T(1)) + T(1);
+    }
+    dr.n2 = wz * (T(1) - px.k) + px.k;        // ndl = l.z
+    dr.nom_raw = Consts<T>::FOUR_PI * dr.n0 * dr.n0 * px.n1 * dr.n2;
+    dr.inv_nom = x_rcp(x_clamp(dr.nom_raw, (T)1e-6, Consts<T>::FOUR_PI));
+    dr.spec = px.alpha2 * dr.F * dr.inv_nom;
+}
+
+// local-frame gradient accumulators: G[a][b] = sum_d ls[d].a * (dL/dl_d).b in frame coordinates,
+// gn = sum_d g_ndh h_d (frame coordinates)
+template <typename T> struct PixelGradL {
+    T Gxx, Gxy, Gxz, Gyx, Gyy, Gyz, Gzx, Gzy, Gzz, gnx, gny, gnz, G_n1, g_alpha2, g_k;
+};
+template <typename T> IRB_HD void pixel_gradl_zero(PixelGradL<T>& g) {
+    g.Gxx = g.Gxy = g.Gxz = g.Gyx = g.Gyy = g.Gyz = g.Gzx = g.Gzy = g.Gzz = T(0);
+    g.gnx = g.gny = g.gnz = g.G_n1 = g.g_alpha2 = g.g_k = T(0);
+}
+
+// g_spec = dL/dspec_d = Omega_d * ndl_d * sum_c gS_c E_cd
+template <typename T>
+IRB_HD void dir_bwd_local(PixelGradL<T>& g, const Pixel<T>& px, const PixelLocal<T>& pl, const DirL<T>& dr, T wx, T wy, T wz,
+                          T g_spec) {
+    const T gsi = g_spec * dr.inv_nom;
+    const T g_F = gsi * px.alpha2;
+    g.g_alpha2 += gsi * dr.F;
+    const bool nom_pass = (dr.nom_raw >= (T)1e-6) && (dr.nom_raw <= Consts<T>::FOUR_PI);
+    const T c4 = nom_pass ? -gsi * dr.spec * Consts<T>::FOUR_PI : T(0);   // g_nom * 4 pi
+    const T x = c4 * dr.n0 * dr.n0;
+    g.G_n1 += x * dr.n2;
+    g.g_k += x * px.n1 * (T(1) - wz);
+    const T g_n0 = c4 * T(2) * dr.n0 * px.n1 * dr.n2;
+    const T g_ndh = g_n0 * T(2) * dr.ndh * (px.alpha2 - T(1));
+    g.g_alpha2 += g_n0 * dr.ndh * dr.ndh;
+    const T g_vdh = g_F * (T(1) - px.F0) * dr.p2 * Consts<T>::LN2 * (T(-2 * 5.55472) * dr.vdh - T(6.98316));
+    const T g_ndhr = (dr.ndh_raw >= T(0) && dr.ndh_raw <= T(1)) ? g_ndh : T(0);
+    // g_h = g_ndhr * n + g_vdh * v   (frame coordinates, n = (0,0,1))
+    const T ghx = g_vdh * pl.vx, ghy = g_vdh * pl.vy, ghz = g_vdh * pl.vz + g_ndhr;
+    const T hx = dr.Mx * dr.rinv, hy = dr.My * dr.rinv, hz = dr.Mz * dr.rinv;
+    g.gnx += g_ndhr * hx;
+    g.gny += g_ndhr * hy;
+    g.gnz += g_ndhr * hz;
+    // h = M * rinv, l = M - v:  dL/dl = (g_h - h (h.g_h)) * rinv   (or g_h * rinv under the m.m clamp)
+    const T hg = dr.mm_ok ? (g_vdh * dr.vdh + g_ndhr * dr.ndh_raw) : T(0);
+    const T glx = (ghx - hx * hg) * dr.rinv, gly = (ghy - hy * hg) * dr.rinv, glz = (ghz - hz * hg) * dr.rinv;
+    g.Gxx += wx * glx; g.Gxy += wx * gly; g.Gxz += wx * glz;
+    g.Gyx += wy * glx; g.Gyy += wy * gly; g.Gyz += wy * glz;
+    g.Gzx += wz * glx; g.Gzy += wz * gly; g.Gzz += wz * glz;
+}
+
+// frame coordinates -> world-space accumulators of the general backward
+template <typename T> IRB_HD void gradl_to_world(PixelGrad<T>& w, const PixelGradL<T>& g, const Pixel<T>& px) {
+    const V3<T>&cx = px.camx, &cy = px.camy, &n = px.n;
+    w.g_cx = V3<T>{g.Gxx * cx.x + g.Gxy * cy.x + g.Gxz * n.x, g.Gxx * cx.y + g.Gxy * cy.y + g.Gxz * n.y,
+                   g.Gxx * cx.z + g.Gxy * cy.z + g.Gxz * n.z};
+    w.g_cy = V3<T>{g.Gyx * cx.x + g.Gyy * cy.x + g.Gyz * n.x, g.Gyx * cx.y + g.Gyy * cy.y + g.Gyz * n.y,
+                   g.Gyx * cx.z + g.Gyy * cy.z + g.Gyz * n.z};
+    const T ax = g.Gzx + g.gnx, ay = g.Gzy + g.gny, az = g.Gzz + g.gnz;
+    w.g_n = V3<T>{ax * cx.x + ay * cy.x + az * n.x, ax * cx.y + ay * cy.y + az * n.y, ax * cx.z + ay * cy.z + az * n.z};
+    w.G_n1 = g.G_n1;
+    w.g_alpha2 = g.g_alpha2;
+    w.g_k = g.g_k;
 }
 
 }  // namespace irb

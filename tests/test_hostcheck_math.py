@@ -120,3 +120,49 @@ def test_unfused_math(lib, path, dbl):
     assert relerr(_pool_bwd(g_alb, z, H, W), z['ref64_g_albedo']) <= tol('g_albedo')
     assert relerr(_pool_bwd(g_nrm, z, H, W), z['ref64_g_normal']) <= tol('g_normal')
     assert relerr(_pool_bwd(g_rg, z, H, W), z['ref64_g_rough']) <= tol('g_rough')
+
+
+@pytest.mark.parametrize('dbl', [1, 0])
+def test_edge_cases_math(lib, dbl):
+    """degenerate frames / clamps / saturated SG parameters (same construction as the GPU edge test)"""
+    B, R, Cc, K = 1, 4, 8, 12
+    ins64 = ro.synth_inputs(B, R, Cc, R, Cc, K, seed=99, dtype=torch.float64)
+    alb, nrm, rg, ax, lam, wt = ins64
+    nrm[0, :, 0, 0] = torch.tensor([0.0, 1.0, 0.0])
+    nrm[0, :, 0, 1] = torch.tensor([0.0, 0.0, 0.0])
+    nrm[0, :, 0, 2] = torch.tensor([0.0, 0.0, -0.9])
+    nrm[0, :, 0, 3] = torch.tensor([0.3, 0.2, 1.2])
+    nrm[0, :, 0, 4] = torch.tensor([0.0, -1.0, 0.0])
+    nrm[0, :, 0, 5] = torch.tensor([0.001, 0.9, 0.002])   # almost parallel to up: badly conditioned frame
+    lam[0, 0] = 1.0
+    wt[0, 0:3] = 1.0
+    lam[0, 1] = 0.0
+    wt[0, 3:6] = 0.0
+    rg[0, 0, 1, :] = -1.0
+    rg[0, 0, 2, :] = 1.0
+    ins64 = [t.float().double().requires_grad_(True) for t in ins64]
+    g = torch.Generator().manual_seed(8)
+    gD = torch.rand(B, 3, R, Cc, generator=g)
+    gS = torch.rand(B, 3, R, Cc, generator=g)
+    d64, s64 = ro.render_sg(*ins64)
+    g64 = torch.autograd.grad((d64 * gD.double()).sum() + (s64 * gS.double()).sum(), ins64)
+    arrs = [t.detach().float().numpy().copy() for t in ins64]
+    ls, ew = ro.env_table()
+    tab = hc.make_tab(ls, ew)
+    view = ro.camera_rays(R, Cc)
+    od = np.zeros((B, 3, R, Cc), np.float32)
+    os_ = np.zeros_like(od)
+    outs = [np.zeros_like(a) for a in arrs]
+    gDn, gSn = gD.numpy(), gS.numpy()
+    a = hc.RenderSgArgs(hc.p(arrs[0]), hc.p(arrs[1]), hc.p(arrs[2]), hc.p(arrs[3]), hc.p(arrs[4]), hc.p(arrs[5]),
+                        hc.p(view), hc.p(od), hc.p(os_), hc.p(gDn), hc.p(gSn), *[hc.p(o) for o in outs],
+                        B, K, R, Cc, 0.05, 1)
+    assert lib.hc_render_sg_fwd(dbl, C.byref(a), C.byref(tab)) == 0
+    assert lib.hc_render_sg_bwd(dbl, C.byref(a), C.byref(tab)) == 0
+    tol = 2e-6 if dbl else 5e-4
+    assert np.isfinite(od).all() and np.isfinite(os_).all()
+    assert relerr(od, d64.detach().numpy()) <= tol
+    assert relerr(os_, s64.detach().numpy()) <= tol
+    for o, t, name in zip(outs, g64, ('albedo', 'normal', 'rough', 'axis', 'lamb', 'weight')):
+        assert np.isfinite(o).all(), name
+        assert relerr(o, t.numpy()) <= tol, name
