@@ -107,7 +107,7 @@ def _best_threads(cores):
     probe a 48-row sample at a few thread counts and keep the fastest -- the baseline gets its best setting."""
     best, best_t = None, 1e30
     step = cpu_step_fn(48)
-    for n in sorted(set([min(cores, x) for x in (8, 16, 32, 64, cores)])):
+    for n in sorted(set([min(cores, x) for x in (4, 8, 16, 32, 64, cores)])):
         torch.set_num_threads(n)
         step()
         t0 = time.perf_counter()
@@ -115,6 +115,8 @@ def _best_threads(cores):
         t = time.perf_counter() - t0
         if t < best_t:
             best, best_t = n, t
+        elif t > 1.25 * best_t:
+            break  # past the scaling knee: more threads only get slower (they collapse at 100+ threads)
     torch.set_num_threads(best)
     return best, best_t / 48
 

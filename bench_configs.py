@@ -1,0 +1,231 @@
+#!/usr/bin/env python
+"""Secondary measurements for DESIGN.md section 8 (NOT the driver's bench contract -- that is bench.py):
+one JSON line per BASELINE.json config that is not the headline.
+
+  python bench_configs.py [--which trainlight,unfused,bilateral,k24,pool,e2e_parts] [--iters 10]
+
+  trainlight : config 2b / 3-geometry: maps 16x240x320 pooled to a 120x160 grid, output2env (env-map
+               materialised for reconstErr) + fused forwardEnv, SG grads only (albedo detached, frozen BRDF nets)
+  unfused    : sg_to_env + render_env fwd/bwd on a materialised env-map (B=4, 240x320), HBM-leaning kernels
+  bilateral  : config 4: BilateralFunction fwd+bwd, 8x480x640, modes 0/2/4
+  k24        : config 5 per-GPU shard: 4 x 480x640, 24 SG lobes, fused fwd+bwd
+All timings: CUDA events on the current stream, median of --iters after 3 warm-ups.
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def timed(fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def rand_inputs(B, H, W, R, C, K, dev, seed):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    alb = torch.rand(B, 3, H, W, device=dev, generator=g)
+    n = torch.randn(B, 3, H, W, device=dev, generator=g)
+    n[:, 2] += 1.5
+    n = n / n.norm(dim=1, keepdim=True)
+    if (H, W) == (R, C):
+        n = n * (0.7 + 0.28 * torch.rand(B, 1, H, W, device=dev, generator=g))
+    rg = torch.rand(B, 1, H, W, device=dev, generator=g) * 2 - 1
+    ax = torch.randn(B, K, 3, R, C, device=dev, generator=g)
+    ax = ax / ax.norm(dim=2, keepdim=True)
+    lam = torch.rand(B, K, R, C, device=dev, generator=g)
+    wt = torch.rand(B, 3 * K, R, C, device=dev, generator=g)
+    return alb, n, rg, ax, lam, wt
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        return float(json.load(open(p))['hbm_gbs'])
+    except Exception:
+        return 6650.0
+
+
+def run_trainlight(models, dev, iters):
+    B, H, W, R, C, K = 16, 240, 320, 120, 160, 12
+    alb, n, rg, ax, lam, wt = rand_inputs(B, H, W, R, C, K, dev, 1236)
+    rl = models.renderingLayer(imWidth=C, imHeight=R, isCuda=True)
+    o2e = models.output2env(K, isCuda=True)
+    im = torch.rand(B, 3, R, C, device=dev)
+    envgt = torch.rand(B, 3, R, C, 8, 16, device=dev)
+
+    def step():
+        a, l, w = [t.detach().requires_grad_(True) for t in (ax, lam, wt)]
+        env, _, _, _ = o2e.output2env(a, l, w)
+        d, s = rl.forwardEnv(alb, n, rg, env)
+        dS, sS = models.LSregressDiffSpec(d.detach(), s.detach(), im, d, s)
+        rerr = ((torch.clamp(dS + sS, 0, 1) - im) ** 2).sum() / (B * R * C) / 3.0
+        rec = ((torch.log(env + 1) - torch.log(envgt + 1)) ** 2).sum() / (B * R * C) / 3.0 / 128
+        (rerr + 10 * rec).backward()
+    ms = timed(step, iters)
+
+    def render_only():
+        a, l, w = [t.detach().requires_grad_(True) for t in (ax, lam, wt)]
+        d, s = rl.forwardSG(alb, n, rg, a, l, w)
+        torch.autograd.backward([d, s], [im, im])
+    ms_r = timed(render_only, iters)
+    npx = B * R * C
+    return {'config': 'trainLight geometry: maps 16x240x320 -> grid 120x160, 12 SG', 'render_loss_step_ms': ms,
+            'fused_render_fwd_bwd_sg_grads_only_ms': ms_r, 'render_Mpix_s': npx / ms_r / 1e3,
+            'note': 'step = output2env (env materialised) + fused forwardEnv + LSregressDiffSpec + render/reconst losses + backward'}
+
+
+def run_unfused(models, dev, iters):
+    B, R, C, K = 4, 240, 320, 12
+    alb, n, rg, ax, lam, wt = rand_inputs(B, R, C, R, C, K, dev, 1237)
+    rl = models.renderingLayer(imWidth=C, imHeight=R, isCuda=True)
+    o2e = models.output2env(K, isCuda=True)
+    npx = B * R * C
+    res = {'config': 'unfused boundary kernels, 4x240x320, 12 SG (env-map 472 MB)'}
+    a, l, w = [t.detach().requires_grad_(True) for t in (ax, lam, wt)]
+    holder = {}
+
+    def f1():
+        holder['env'] = o2e.output2env(a, l, w)[0]
+    res['sg_to_env_fwd_ms'] = timed(f1, iters)
+    env = holder['env']
+    genv = torch.rand_like(env)
+
+    def f2():
+        torch.autograd.grad(env, [a, l, w], genv, retain_graph=True)
+    res['sg_to_env_bwd_ms'] = timed(f2, iters)
+    envp = env.detach().clone().requires_grad_(True)
+    leaves = [t.detach().requires_grad_(True) for t in (alb, n, rg)]
+
+    def f3():
+        holder['ds'] = rl.forwardEnv(leaves[0], leaves[1], leaves[2], envp)
+    res['render_env_fwd_ms'] = timed(f3, iters)
+    d, s = holder['ds']
+    g1 = torch.rand_like(d)
+
+    def f4():
+        torch.autograd.grad([d, s], leaves + [envp], [g1, g1], retain_graph=True)
+    res['render_env_bwd_ms'] = timed(f4, iters)
+    pk = peak_hbm()
+    byt = {'sg_to_env_fwd': (11 * K + 384) * 4, 'sg_to_env_bwd': (384 + 14 * K) * 4, 'render_env_fwd': (384 + 13) * 4,
+           'render_env_bwd': (2 * 384 + 20) * 4}
+    for k, bpp in byt.items():
+        gbs = bpp * npx / (res[k + '_ms'] * 1e-3) / 1e9
+        res[k + '_GBs'] = gbs
+        res[k + '_hbm_frac'] = gbs / pk
+    return res
+
+
+def run_bilateral(BL, dev, iters):
+    from oracle import bilateral_oracle as bo  # synthetic guide generator only (test infrastructure)
+    B, H, W = 8, 480, 640
+    guide = torch.from_numpy(bo.synth_guide(B, H, W, blur_sigma=8.0, seed=1238)).to(dev)
+    out = {'config': 'BilateralFunction fwd+bwd, 8x480x640'}
+    for mode, ch in ((0, 3), (2, 1), (4, 1)):
+        sig, bsp = BL._PRESETS[mode]
+        gp = torch.tensor([float(x) for x in sig], device=dev)
+        bp = torch.tensor([float(x) for x in bsp], device=dev)
+        pred = torch.rand(B, ch, H, W, device=dev)
+        conf = 0.05 + 0.95 * torch.rand(B, 1, H, W, device=dev)
+        gout = torch.randn(B, ch, H, W, device=dev)
+        holder = {}
+
+        def fwd():
+            p = pred.detach().requires_grad_(True)
+            c = conf.detach().requires_grad_(True)
+            o, _ = BL.BilateralFunction.apply(guide, p, c, gp, bp)
+            holder['x'] = (o, p, c)
+
+        def fwdbwd():
+            fwd()
+            o, p, c = holder['x']
+            torch.autograd.grad(o, [p, c], gout)
+        f = timed(fwd, iters)
+        fb = timed(fwdbwd, iters)
+        out['mode%d' % mode] = {'ch': ch, 'fwd_ms': f, 'fwd_bwd_ms': fb, 'Mpix_s_fwd_bwd': B * H * W / fb / 1e3}
+    return out
+
+
+def run_k24(models, dev, iters):
+    B, R, C, K = 4, 480, 640, 24
+    alb, n, rg, ax, lam, wt = rand_inputs(B, R, C, R, C, K, dev, 1238)
+    rl = models.renderingLayer(imWidth=C, imHeight=R, isCuda=True)
+    g1 = torch.rand(B, 3, R, C, device=dev)
+    holder = {}
+
+    def fwd():
+        leaves = [t.detach().requires_grad_(True) for t in (alb, n, rg, ax, lam, wt)]
+        holder['x'] = (rl.forwardSG(*leaves), leaves)
+
+    def fwdbwd():
+        fwd()
+        (d, s), leaves = holder['x']
+        torch.autograd.backward([d, s], [g1, g1])
+    f = timed(fwd, iters)
+    fb = timed(fwdbwd, iters)
+    return {'config': 'config 5 per-GPU shard: 4x480x640, 24 SG, fused fwd+bwd all grads', 'fwd_ms': f, 'fwd_bwd_ms': fb,
+            'Mpix_s': B * R * C / fb / 1e3}
+
+
+def run_torchcuda(dev, iters):
+    """the oracle port (PyTorch op graph, direction-by-direction restatement of the reference) on the SAME GPU:
+    what a torch-CUDA implementation of the layer costs next to the fused kernel (a comparator, not product)."""
+    from oracle import render_oracle as ro
+    B, R, C, K = 2, 240, 320, 12
+    alb, n, rg, ax, lam, wt = rand_inputs(B, R, C, R, C, K, dev, 1239)
+    g1 = torch.rand(B, 3, R, C, device=dev)
+
+    def step():
+        leaves = [t.detach().requires_grad_(True) for t in (alb, n, rg, ax, lam, wt)]
+        d, s = ro.render_sg(*leaves)
+        torch.autograd.backward([d, s], [g1, g1])
+    ms = timed(step, max(3, iters // 3), warm=1)
+    return {'config': 'oracle port as a torch-CUDA op graph, 2x240x320, 12 SG, fwd+bwd all grads', 'fwd_bwd_ms': ms,
+            'Mpix_s': B * R * C / ms / 1e3}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--which', default='trainlight,unfused,bilateral,k24,torchcuda')
+    ap.add_argument('--iters', type=int, default=10)
+    args = ap.parse_args()
+    from inverserenderingofindoorscene_b200 import BilateralLayer as BL
+    from inverserenderingofindoorscene_b200 import _lib, models
+    _lib.lib()
+    dev = torch.device('cuda', 0)
+    for w in args.which.split(','):
+        if w == 'trainlight':
+            r = run_trainlight(models, dev, args.iters)
+        elif w == 'unfused':
+            r = run_unfused(models, dev, args.iters)
+        elif w == 'bilateral':
+            r = run_bilateral(BL, dev, args.iters)
+        elif w == 'k24':
+            r = run_k24(models, dev, args.iters)
+        elif w == 'torchcuda':
+            r = run_torchcuda(dev, args.iters)
+        else:
+            continue
+        print(json.dumps(r))
+        sys.stdout.flush()
+
+
+if __name__ == '__main__':
+    main()

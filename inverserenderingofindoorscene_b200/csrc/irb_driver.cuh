@@ -81,38 +81,49 @@ IRB_HD void load_pixel(Pixel<T>& px, V3<T>& nt, T (&A)[3], const RenderSgArgs& a
     pixel_setup(px, nt, (T)a.rough[b * plane + pix], v, (T)a.F0);
 }
 
+// A driver call reads its inputs through an INPUT VIEW (ai, bi, pi, pli) and writes through an OUTPUT VIEW
+// (a, b, pix, plane).  The plain kernels and tests/hostcheck pass the same view twice (global tensors);
+// the TMA-staged persistent kernels pass a view of the shared-memory stage as the input view.
+struct PixView {
+    size_t b, pix, plane;
+};
+
 // ---- forward: out_diff, out_spec --------------------------------------------------------
 template <typename T, int KC>
-IRB_HD void drv_render_sg_fwd(const RenderSgArgs& a, const EnvTab& tab, size_t b, size_t pix) {
-    const size_t plane = (size_t)a.R * a.C;
+IRB_HD void drv_render_sg_fwd(const RenderSgArgs& ai, const PixView& vi, const RenderSgArgs& a, const PixView& vo, const EnvTab& tab) {
     Pixel<T> px;
     V3<T> nt;
     T A[3];
-    load_pixel(px, nt, A, a, b, pix, plane);
+    load_pixel(px, nt, A, ai, vi.b, vi.pix, vi.plane);
     T Dc[3] = {0, 0, 0}, Sc[3] = {0, 0, 0};
-    for (int k0 = 0; k0 < a.K; k0 += KC) {
+    for (int k0 = 0; k0 < ai.K; k0 += KC) {
         Lobes<T, KC> L;
-        load_lobes(L, a, b, pix, plane, k0);
+        load_lobes(L, ai, vi.b, vi.pix, vi.plane, k0);
         T U[KC], V[KC];
         sweep_fwd<T, KC>(px, L, tab, U, V);
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
-            if (k0 + k < a.K) {
+            if (k0 + k < ai.K) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const T w = load_weight<T>(a, b, pix, plane, k0 + k, c);
+                    const T w = load_weight<T>(ai, vi.b, vi.pix, vi.plane, k0 + k, c);
                     Dc[c] += w * U[k];
                     Sc[c] += w * V[k];
                 }
             }
         }
     }
-    const size_t o3 = (b * 3) * plane + pix;
+    const size_t o3 = (vo.b * 3) * vo.plane + vo.pix;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        a.out_diff[o3 + c * plane] = (float)(A[c] * Consts<T>::INV_PI * Dc[c]);
-        a.out_spec[o3 + c * plane] = (float)Sc[c];
+        a.out_diff[o3 + c * vo.plane] = (float)(A[c] * Consts<T>::INV_PI * Dc[c]);
+        a.out_spec[o3 + c * vo.plane] = (float)Sc[c];
     }
+}
+template <typename T, int KC>
+IRB_HD void drv_render_sg_fwd(const RenderSgArgs& a, const EnvTab& tab, size_t b, size_t pix) {
+    const PixView v{b, pix, (size_t)a.R * a.C};
+    drv_render_sg_fwd<T, KC>(a, v, a, v, tab);
 }
 
 // ---- backward -----------------------------------------------------------------------------
@@ -137,33 +148,34 @@ IRB_HD void load_PQ(T (&P)[KC], T (&Q)[KC], const RenderSgArgs& a, size_t b, siz
 
 template <typename T, int KC>
 IRB_HD void store_lobe_grads(const LobeGrads<T, KC>& lg, const Lobes<T, KC>& L, const T (&P)[KC], const T (&Q)[KC],
-                             const RenderSgArgs& a, size_t b, size_t pix, size_t plane, int k0, const T (&gDa)[3],
-                             const T (&gS)[3], T (&gAlb)[3]) {
+                             const RenderSgArgs& ai, const PixView& vi, const RenderSgArgs& a, const PixView& vo, int k0,
+                             const T (&gDa)[3], const T (&gS)[3], T (&gAlb)[3]) {
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
         const int kk = k0 + k;
         if (kk < a.K) {
             const T lam = L.lam[k] * Consts<T>::LN2;  // undo the log2e fold
-            const size_t oa = ((b * a.K + kk) * 3) * plane + pix;
+            const size_t oa = ((vo.b * a.K + kk) * 3) * vo.plane + vo.pix;
             if (a.g_axis) {
                 a.g_axis[oa] = (float)(lam * lg.mx[k]);
-                a.g_axis[oa + plane] = (float)(lam * lg.my[k]);
-                a.g_axis[oa + 2 * plane] = (float)(lam * lg.mz[k]);
+                a.g_axis[oa + vo.plane] = (float)(lam * lg.my[k]);
+                a.g_axis[oa + 2 * vo.plane] = (float)(lam * lg.mz[k]);
             }
             if (a.g_lamb) {
+                const size_t ia = ((vi.b * ai.K + kk) * 3) * vi.plane + vi.pix;
                 T g = lobe_lam_grad<T>(lg.S[k], L.lam[k], lg.mx[k], lg.my[k], lg.mz[k], P[k] * lg.U[k] + Q[k] * lg.V[k],
-                                       a.axis, oa, plane);
+                                       ai.axis, ia, vi.plane);
                 if (a.warp) g *= sg_warp_grad<T>(lam);
-                a.g_lamb[(b * a.K + kk) * plane + pix] = (float)g;
+                a.g_lamb[(vo.b * a.K + kk) * vo.plane + vo.pix] = (float)g;
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const T w = load_weight<T>(a, b, pix, plane, kk, c);
+                const T w = load_weight<T>(ai, vi.b, vi.pix, vi.plane, kk, c);
                 gAlb[c] += w * lg.U[k];
                 if (a.g_weight) {
                     T g = gDa[c] * lg.U[k] + gS[c] * lg.V[k];
                     if (a.warp) g *= sg_warp_grad<T>(w);
-                    a.g_weight[(b * (3 * a.K) + 3 * kk + c) * plane + pix] = (float)g;
+                    a.g_weight[(vo.b * (3 * a.K) + 3 * kk + c) * vo.plane + vo.pix] = (float)g;
                 }
             }
         }
@@ -171,18 +183,18 @@ IRB_HD void store_lobe_grads(const LobeGrads<T, KC>& lg, const Lobes<T, KC>& L, 
 }
 
 template <typename T, int KP, int KL, bool PIX, bool LOBE>
-IRB_HD void drv_render_sg_bwd(const RenderSgArgs& a, const EnvTab& tab, size_t b, size_t pix) {
-    const size_t plane = (size_t)a.R * a.C;
+IRB_HD void drv_render_sg_bwd(const RenderSgArgs& ai, const PixView& vi, const RenderSgArgs& a, const PixView& vo, const EnvTab& tab) {
     Pixel<T> px;
     V3<T> nt;
     T A[3];
-    load_pixel(px, nt, A, a, b, pix, plane);
-    const size_t o3 = (b * 3) * plane + pix;
+    load_pixel(px, nt, A, ai, vi.b, vi.pix, vi.plane);
+    const size_t i3 = (vi.b * 3) * vi.plane + vi.pix;
+    const size_t o3 = (vo.b * 3) * vo.plane + vo.pix;
     T gD[3], gS[3], gDa[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        gD[c] = (T)a.g_diff[o3 + c * plane];
-        gS[c] = (T)a.g_spec[o3 + c * plane];
+        gD[c] = (T)ai.g_diff[i3 + c * vi.plane];
+        gS[c] = (T)ai.g_spec[i3 + c * vi.plane];
         gDa[c] = gD[c] * A[c] * Consts<T>::INV_PI;
     }
     PixelGrad<T> pg;
@@ -191,30 +203,30 @@ IRB_HD void drv_render_sg_bwd(const RenderSgArgs& a, const EnvTab& tab, size_t b
     if (KP == KL) {
         // single sweep: all lobes in one chunk
         Lobes<T, KP> L;
-        load_lobes(L, a, b, pix, plane, 0);
+        load_lobes(L, ai, vi.b, vi.pix, vi.plane, 0);
         T P[KP], Q[KP];
-        load_PQ<T, KP>(P, Q, a, b, pix, plane, 0, gDa, gS);
+        load_PQ<T, KP>(P, Q, ai, vi.b, vi.pix, vi.plane, 0, gDa, gS);
         LobeGrads<T, KP> lg;
         sweep_bwd<T, KP, PIX, LOBE>(px, L, P, Q, tab, pg, lg);
-        if (LOBE) store_lobe_grads<T, KP>(lg, L, P, Q, a, b, pix, plane, 0, gDa, gS, gAlb);
+        if (LOBE) store_lobe_grads<T, KP>(lg, L, P, Q, ai, vi, a, vo, 0, gDa, gS, gAlb);
     } else {
         if (PIX) {
             Lobes<T, KP> L;
-            load_lobes(L, a, b, pix, plane, 0);
+            load_lobes(L, ai, vi.b, vi.pix, vi.plane, 0);
             T P[KP], Q[KP];
-            load_PQ<T, KP>(P, Q, a, b, pix, plane, 0, gDa, gS);
+            load_PQ<T, KP>(P, Q, ai, vi.b, vi.pix, vi.plane, 0, gDa, gS);
             LobeGrads<T, KP> lg;  // unused
             sweep_bwd<T, KP, true, false>(px, L, P, Q, tab, pg, lg);
         }
         if (LOBE) {
             for (int k0 = 0; k0 < a.K; k0 += KL) {
                 Lobes<T, KL> L;
-                load_lobes(L, a, b, pix, plane, k0);
+                load_lobes(L, ai, vi.b, vi.pix, vi.plane, k0);
                 T P[KL], Q[KL];
-                load_PQ<T, KL>(P, Q, a, b, pix, plane, k0, gDa, gS);
+                load_PQ<T, KL>(P, Q, ai, vi.b, vi.pix, vi.plane, k0, gDa, gS);
                 LobeGrads<T, KL> lg;
                 sweep_bwd<T, KL, false, true>(px, L, P, Q, tab, pg, lg);
-                store_lobe_grads<T, KL>(lg, L, P, Q, a, b, pix, plane, k0, gDa, gS, gAlb);
+                store_lobe_grads<T, KL>(lg, L, P, Q, ai, vi, a, vo, k0, gDa, gS, gAlb);
             }
         }
     }
@@ -224,15 +236,20 @@ IRB_HD void drv_render_sg_bwd(const RenderSgArgs& a, const EnvTab& tab, size_t b
         pixel_bwd_finish(pg, px, nt, g_nt, g_rough);
         if (a.g_normal) {
             a.g_normal[o3] = (float)g_nt.x;
-            a.g_normal[o3 + plane] = (float)g_nt.y;
-            a.g_normal[o3 + 2 * plane] = (float)g_nt.z;
+            a.g_normal[o3 + vo.plane] = (float)g_nt.y;
+            a.g_normal[o3 + 2 * vo.plane] = (float)g_nt.z;
         }
-        if (a.g_rough) a.g_rough[b * plane + pix] = (float)g_rough;
+        if (a.g_rough) a.g_rough[vo.b * vo.plane + vo.pix] = (float)g_rough;
     }
     if (LOBE && a.g_albedo) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) a.g_albedo[o3 + c * plane] = (float)(gD[c] * Consts<T>::INV_PI * gAlb[c]);
+        for (int c = 0; c < 3; ++c) a.g_albedo[o3 + c * vo.plane] = (float)(gD[c] * Consts<T>::INV_PI * gAlb[c]);
     }
+}
+template <typename T, int KP, int KL, bool PIX, bool LOBE>
+IRB_HD void drv_render_sg_bwd(const RenderSgArgs& a, const EnvTab& tab, size_t b, size_t pix) {
+    const PixView v{b, pix, (size_t)a.R * a.C};
+    drv_render_sg_bwd<T, KP, KL, PIX, LOBE>(a, v, a, v, tab);
 }
 
 }  // namespace irb

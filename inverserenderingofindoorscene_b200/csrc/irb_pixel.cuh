@@ -49,6 +49,7 @@ IRB_HD void sweep_fwd(const Pixel<T>& px, const Lobes<T, KC>& L, const EnvTab& t
     if (px.regular) {
         PixelLocal<T> pl;
         pixel_local_setup(pl, px);
+#pragma unroll 2
         for (int d = 0; d < tab.D; ++d) {
             const T wx = (T)tab.lx[d], wy = (T)tab.ly[d], wz = (T)tab.lz[d];
             DirL<T> dr;

@@ -2,19 +2,35 @@
 // (replaces models.output2env.output2env + models.renderingLayer.forwardEnv,
 // models.py:371-404 and 466-520, without materialising the [B,3,R,C,8,16] env-map).
 //
-// Mapping: one thread per render-grid pixel, 128-thread CTAs, grid = (ceil(R*C/128), B).
-// All tensors are channel-planar [B,ch,R,C], so the warp's 32 pixels read/write 128 contiguous
-// bytes per plane (fully coalesced, each byte of HBM traffic touched exactly once).  The lobe
-// parameters, their gradient accumulators and the BRDF state are register-resident for the whole
-// 128-direction sweep; the hemisphere table lives in the kernel-parameter constant bank.
-// The kernel is FP32-FMA / MUFU bound: ~100 FLOP per HBM byte.
+// Mapping: one thread per render-grid pixel; all tensors are channel-planar [B,ch,R,C], so a tile of
+// 128 consecutive pixels is 128 contiguous floats (512 B) in every plane.
+//
+// Primary path: PERSISTENT, TMA-STAGED kernels.  grid = (#SM x resident CTAs); each 128-thread CTA
+// walks tiles of 128 pixels.  The 16+7K input planes of a tile (BRDF maps, view vectors, SG lobes,
+// upstream gradients) are staged into shared memory by bulk async copies (cp.async.bulk ->
+// UBLKCP, completion on an mbarrier) into a 2-stage ring: the copies of tile t+1 are issued before
+// the direction sweep of tile t starts, so the ~100 plane reads a pixel needs never sit on the critical
+// path (the non-staged kernel spent ~45 % of its time in long-scoreboard stalls on exactly those reads
+// with the 2 warps/scheduler that 250 registers/thread allow; profiles/r01).  Each byte is read from
+// HBM exactly once; results go back with coalesced 128-byte stores straight from registers.
+// The sweep itself (lobes, gradient accumulators, BRDF state) is register-resident; the hemisphere
+// table lives in the kernel-parameter constant bank.  FP32-FMA / MUFU bound.
+//
+// Fallback path (same math, same results): plain one-thread-per-pixel kernels with direct global
+// loads, used when a plane is not 16-byte addressable (R*C % 4 != 0 or misaligned base pointers).
+#include <stdint.h>
+
 #include "irb_common.cuh"
 #include "irb_driver.cuh"
 
 namespace irb {
 
 constexpr int kThreads = 128;
+constexpr int kTile = 128;  // pixels per tile = threads per CTA
 
+// ---------------------------------------------------------------------------------------------
+// plain kernels (fallback)
+// ---------------------------------------------------------------------------------------------
 template <int KC>
 __global__ void __launch_bounds__(kThreads) render_sg_fwd_kernel(const RenderSgArgs a, const __grid_constant__ EnvTab tab) {
     const size_t pix = (size_t)blockIdx.x * kThreads + threadIdx.x;
@@ -27,6 +43,165 @@ __global__ void __launch_bounds__(kThreads) render_sg_bwd_kernel(const RenderSgA
     const size_t pix = (size_t)blockIdx.x * kThreads + threadIdx.x;
     if (pix >= (size_t)a.R * a.C) return;
     drv_render_sg_bwd<float, KP, KL, PIX, LOBE>(a, tab, blockIdx.y, pix);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA / mbarrier primitives (PTX; SASS: UBLKCP, SYNCS)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; !ok; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!ok && spin > (1u << 26)) __trap();  // a lost copy must fail the launch, never hang the GPU
+    }
+}
+
+// plane order inside a stage (each plane = kTile floats): albedo 3 | normal 3 | rough 1 | view 3 |
+// axis 3K | lamb K | weight 3K | g_diff 3 | g_spec 3 (backward only)
+__host__ __device__ inline int stage_planes(int K, bool bwd) { return 10 + 7 * K + (bwd ? 6 : 0); }
+
+// Issue the bulk copies of one tile (executed by warp 0; lanes split the planes).
+__device__ __forceinline__ void issue_tile(float* stage, uint64_t* bar, const RenderSgArgs& a, size_t tile, size_t tiles_per_img,
+                                           bool bwd) {
+    const int lane = threadIdx.x & 31;
+    const size_t plane = (size_t)a.R * a.C;
+    const size_t b = tile / tiles_per_img, pix0 = (tile % tiles_per_img) * kTile;
+    const uint32_t valid = (uint32_t)((plane - pix0) < (size_t)kTile ? (plane - pix0) : (size_t)kTile);
+    const uint32_t bytes = valid * 4u;  // multiple of 16: the launcher requires plane % 4 == 0
+    const int K = a.K;
+    const int np = stage_planes(K, bwd);
+    if (lane == 0) mbar_expect_tx(bar, bytes * (uint32_t)np);
+    __syncwarp();
+    for (int p = lane; p < np; p += 32) {
+        const float* src;
+        if (p < 3) src = a.albedo + (b * 3 + p) * plane;
+        else if (p < 6) src = a.normal + (b * 3 + (p - 3)) * plane;
+        else if (p < 7) src = a.rough + b * plane;
+        else if (p < 10) src = a.view + (size_t)(p - 7) * plane;
+        else if (p < 10 + 3 * K) src = a.axis + (b * 3 * K + (p - 10)) * plane;
+        else if (p < 10 + 4 * K) src = a.lamb + (b * K + (p - 10 - 3 * K)) * plane;
+        else if (p < 10 + 7 * K) src = a.weight + (b * 3 * K + (p - 10 - 4 * K)) * plane;
+        else if (p < 13 + 7 * K) src = a.g_diff + (b * 3 + (p - 10 - 7 * K)) * plane;
+        else src = a.g_spec + (b * 3 + (p - 13 - 7 * K)) * plane;
+        bulk_g2s(stage + (size_t)p * kTile, src + pix0, bytes, bar);
+    }
+}
+
+// input view of a stage: same field meaning as the global tensors, with b = 0, plane = kTile
+__device__ __forceinline__ RenderSgArgs stage_view(const RenderSgArgs& a, float* stage) {
+    RenderSgArgs s = a;
+    const int K = a.K;
+    s.albedo = stage;
+    s.normal = stage + 3 * kTile;
+    s.rough = stage + 6 * kTile;
+    s.view = stage + 7 * kTile;
+    s.axis = stage + 10 * kTile;
+    s.lamb = stage + (10 + 3 * K) * kTile;
+    s.weight = stage + (10 + 4 * K) * kTile;
+    s.g_diff = stage + (10 + 7 * K) * kTile;
+    s.g_spec = stage + (13 + 7 * K) * kTile;
+    return s;
+}
+
+// MODE 0: forward<KP>; MODE 1: backward<KP,KL,PIX,LOBE>
+template <int MODE, int KP, int KL, bool PIX, bool LOBE>
+__global__ void __launch_bounds__(kThreads) render_sg_tma_kernel(const RenderSgArgs a, const __grid_constant__ EnvTab tab,
+                                                                  const unsigned total_tiles, const unsigned tiles_per_img) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[2];
+    constexpr bool BWD = (MODE == 1);
+    const int np = stage_planes(a.K, BWD);
+    float* stage[2] = {reinterpret_cast<float*>(smem_raw), reinterpret_cast<float*>(smem_raw) + (size_t)np * kTile};
+    if (threadIdx.x == 0) {
+        mbar_init(&full_bar[0], 1);
+        mbar_init(&full_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const size_t plane = (size_t)a.R * a.C;
+    unsigned t = blockIdx.x;
+    if (t < total_tiles && threadIdx.x < 32) issue_tile(stage[0], &full_bar[0], a, t, tiles_per_img, BWD);
+    for (unsigned it = 0; t < total_tiles; ++it, t += gridDim.x) {
+        const int s = it & 1;
+        const unsigned tn = t + gridDim.x;
+        if (tn < total_tiles && threadIdx.x < 32) {
+            // stage s^1 was last read (generic proxy) in iteration it-1, which ended with __syncthreads()
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue_tile(stage[s ^ 1], &full_bar[s ^ 1], a, tn, tiles_per_img, BWD);
+        }
+        mbar_wait(&full_bar[s], (it >> 1) & 1);
+        const size_t b = t / tiles_per_img, pix0 = (size_t)(t % tiles_per_img) * kTile;
+        if (pix0 + threadIdx.x < plane) {
+            const RenderSgArgs sv = stage_view(a, stage[s]);
+            const PixView vi{0, threadIdx.x, (size_t)kTile};
+            const PixView vo{b, pix0 + threadIdx.x, plane};
+            if (MODE == 0) drv_render_sg_fwd<float, KP>(sv, vi, a, vo, tab);
+            else drv_render_sg_bwd<float, KP, KL, PIX, LOBE>(sv, vi, a, vo, tab);
+        }
+        __syncthreads();  // everyone is done with stage s before it is refilled (iteration it+1 issues into it)
+    }
+}
+
+struct Launch {
+    int sms = 0;
+};
+
+static int device_sms() {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms > 0 ? sms : 148;
+}
+
+static bool tma_ok(const RenderSgArgs& a, bool bwd) {
+    const size_t plane = (size_t)a.R * a.C;
+    if (plane % 4 != 0) return false;
+    const void* ptrs[] = {a.albedo, a.normal, a.rough, a.view, a.axis, a.lamb, a.weight, bwd ? a.g_diff : a.albedo,
+                          bwd ? a.g_spec : a.albedo};
+    for (const void* p : ptrs)
+        if (((uintptr_t)p & 15u) != 0) return false;
+    return true;
+}
+
+template <typename KernelT>
+static int launch_tma(KernelT kernel, const RenderSgArgs& a, const EnvTab& tab, bool bwd, cudaStream_t st, const char* what) {
+    const size_t plane = (size_t)a.R * a.C;
+    const size_t tiles_per_img = (plane + kTile - 1) / kTile;
+    const size_t total = tiles_per_img * (size_t)a.B;
+    if (total >= 0xffffffffull) {
+        set_error("%s: too many tiles", what);
+        return IRB_E_UNSUPPORTED;
+    }
+    const size_t smem = 2 * (size_t)stage_planes(a.K, bwd) * kTile * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", what, smem, cudaGetErrorString(e));
+        return (int)e;
+    }
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem);
+    if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+    size_t grid = (size_t)device_sms() * per_sm;
+    if (grid > total) grid = total;
+    kernel<<<(unsigned)grid, kThreads, smem, st>>>(a, tab, (unsigned)total, (unsigned)tiles_per_img);
+    return check_launch(what);
 }
 
 static int check_common(const RenderSgArgs& a, int envH, int envW, EnvTab& tab) {
@@ -62,8 +237,12 @@ extern "C" int irb_render_sg_fwd(const float* albedo, const float* normal, const
     EnvTab tab;
     if (int rc = check_common(a, envH, envW, tab)) return rc;
     IRB_REQUIRE(out_diff && out_spec, "render_sg_fwd: null output pointer");
-    const dim3 grid((unsigned)(((size_t)R * C + kThreads - 1) / kThreads), (unsigned)B);
     cudaStream_t st = (cudaStream_t)stream;
+    if (tma_ok(a, false)) {
+        if (K <= 12) return launch_tma(render_sg_tma_kernel<0, 12, 12, false, false>, a, tab, false, st, "render_sg_fwd(tma)");
+        return launch_tma(render_sg_tma_kernel<0, 24, 24, false, false>, a, tab, false, st, "render_sg_fwd(tma)");
+    }
+    const dim3 grid((unsigned)(((size_t)R * C + kThreads - 1) / kThreads), (unsigned)B);
     if (K <= 12) render_sg_fwd_kernel<12><<<grid, kThreads, 0, st>>>(a, tab);
     else render_sg_fwd_kernel<24><<<grid, kThreads, 0, st>>>(a, tab);
     return check_launch("render_sg_fwd");
@@ -85,8 +264,19 @@ extern "C" int irb_render_sg_bwd(const float* albedo, const float* normal, const
     const bool pix = g_normal || g_rough;
     const bool lobe = g_axis || g_lamb || g_weight || g_albedo;
     if (!pix && !lobe) return 0;
-    const dim3 grid((unsigned)(((size_t)R * C + kThreads - 1) / kThreads), (unsigned)B);
     cudaStream_t st = (cudaStream_t)stream;
+    if (tma_ok(a, true)) {
+        const char* w = "render_sg_bwd(tma)";
+        if (K <= 12) {
+            if (pix && lobe) return launch_tma(render_sg_tma_kernel<1, 12, 12, true, true>, a, tab, true, st, w);
+            if (pix) return launch_tma(render_sg_tma_kernel<1, 12, 12, true, false>, a, tab, true, st, w);
+            return launch_tma(render_sg_tma_kernel<1, 12, 12, false, true>, a, tab, true, st, w);
+        }
+        if (pix && lobe) return launch_tma(render_sg_tma_kernel<1, 24, 12, true, true>, a, tab, true, st, w);
+        if (pix) return launch_tma(render_sg_tma_kernel<1, 24, 12, true, false>, a, tab, true, st, w);
+        return launch_tma(render_sg_tma_kernel<1, 24, 12, false, true>, a, tab, true, st, w);
+    }
+    const dim3 grid((unsigned)(((size_t)R * C + kThreads - 1) / kThreads), (unsigned)B);
     if (K <= 12) {
         if (pix && lobe) render_sg_bwd_kernel<12, 12, true, true><<<grid, kThreads, 0, st>>>(a, tab);
         else if (pix) render_sg_bwd_kernel<12, 12, true, false><<<grid, kThreads, 0, st>>>(a, tab);

@@ -83,7 +83,7 @@ def sg_to_env(axis, lamb, weight, envHeight=8, envWidth=16):
     B, K = axis.shape[0], axis.shape[1]
     R, C = axis.shape[3], axis.shape[4]
     ls, _ = env_table(envHeight, envWidth)
-    ls = torch.from_numpy(ls).to(axis.dtype)
+    ls = torch.from_numpy(ls).to(device=axis.device, dtype=axis.dtype)
     D = ls.shape[0]
     w = weight.reshape(B, K, 3, R, C)
     out = []
@@ -124,9 +124,10 @@ def render_env(albedo, normal, rough, envmap, fov=57.0, F0=0.05, cameraPos=(0.0,
     envH, envW = envmap.shape[4], envmap.shape[5]
     D = envH * envW
     ls_np, ew_np = env_table(envH, envW)
-    ls = torch.from_numpy(ls_np).to(dt)
-    ew = torch.from_numpy(ew_np).to(dt)
-    v = (torch.from_numpy(camera_rays(R, C, fov, cameraPos)) if view is None else view).to(dt)  # [3,R,C]
+    dev = envmap.device
+    ls = torch.from_numpy(ls_np).to(device=dev, dtype=dt)
+    ew = torch.from_numpy(ew_np).to(device=dev, dtype=dt)
+    v = (torch.from_numpy(camera_rays(R, C, fov, cameraPos)) if view is None else view).to(device=dev, dtype=dt)  # [3,R,C]
 
     # models.py:465-469
     A = F.adaptive_avg_pool2d(albedo, (R, C))
@@ -135,7 +136,7 @@ def render_env(albedo, normal, rough, envmap, fov=57.0, F0=0.05, cameraPos=(0.0,
     rg = F.adaptive_avg_pool2d(rough, (R, C))
 
     # models.py:477-480: local frame
-    up = torch.tensor([0.0, 1.0, 0.0], dtype=dt).view(1, 3, 1, 1)
+    up = torch.tensor([0.0, 1.0, 0.0], dtype=dt, device=dev).view(1, 3, 1, 1)
     upn = n[:, 1:2]  # up . n
     camy = _normalize(up - upn * n, dim=1)
     camx = -_normalize(torch.cross(camy, n, dim=1), dim=1)
@@ -148,9 +149,9 @@ def render_env(albedo, normal, rough, envmap, fov=57.0, F0=0.05, cameraPos=(0.0,
     ndv = torch.clamp((n * vv).sum(dim=1, keepdim=True), 0, 1)
 
     env = envmap.reshape(B, 3, R, C, D)
-    cd = torch.zeros(B, 3, R, C, dtype=dt)
-    cs = torch.zeros(B, 3, R, C, dtype=dt)
-    two = torch.tensor(2.0, dtype=dt)
+    cd = torch.zeros(B, 3, R, C, dtype=dt, device=dev)
+    cs = torch.zeros(B, 3, R, C, dtype=dt, device=dev)
+    two = torch.tensor(2.0, dtype=dt, device=dev)
     for d in range(D):
         # models.py:482-484
         l = ls[d, 0] * camx + ls[d, 1] * camy + ls[d, 2] * n
