@@ -155,8 +155,8 @@ def test_full_size_properties(irb):
     sl = slice(0, 4)
     env = o2e.fromSGtoIm(ax[sl].contiguous(), lam[sl].contiguous(), wt[sl].contiguous())
     du, su = rl.forwardEnv(alb[sl], n[sl], rg[sl], env)
-    assert relerr(du.cpu().numpy(), d1[sl].cpu().numpy()) <= 2e-5
-    assert relerr(su.cpu().numpy(), s1[sl].cpu().numpy()) <= 2e-5
+    assert relerr(du.cpu().numpy(), d1[sl].cpu().numpy()) <= 1e-5
+    assert relerr(su.cpu().numpy(), s1[sl].cpu().numpy()) <= 1e-4   # general-path vs local-frame fp32 round-off at the GGX peak
     # gradient dot-test at full size: <J^T g, dx> == <g, J dx> by central differences along one smooth
     # direction (roughness kept away from the mirror limit where the GGX peak makes finite differences useless)
     lam_r = torch.rand(B, K, R, C, device=dev, generator=g) * 0.8
