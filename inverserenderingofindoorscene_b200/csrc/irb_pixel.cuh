@@ -49,30 +49,19 @@ IRB_HD void sweep_fwd(const Pixel<T>& px, const Lobes<T, KC>& L, const EnvTab& t
     if (px.regular) {
         PixelLocal<T> pl;
         pixel_local_setup(pl, px);
-        // software pipeline: the (serial) BRDF chain of direction d+1 is independent of the 12 lobe
-        // chains of direction d, so it is issued in the same iteration and hides behind them
-        T w, ws;
-        {
-            DirL<T> dr;
-            dir_fwd_local(dr, px, pl, (T)tab.lx[0], (T)tab.ly[0], (T)tab.lz[0]);
-            w = (T)tab.w[0] * (T)tab.lz[0];
-            ws = w * dr.spec;
-        }
+#pragma unroll 2
         for (int d = 0; d < tab.D; ++d) {
             const T wx = (T)tab.lx[d], wy = (T)tab.ly[d], wz = (T)tab.lz[d];
-            const int dn = d + 1 < tab.D ? d + 1 : d;
-            DirL<T> drn;
-            dir_fwd_local(drn, px, pl, (T)tab.lx[dn], (T)tab.ly[dn], (T)tab.lz[dn]);
-            const T wn = (T)tab.w[dn] * (T)tab.lz[dn];
-            const T wsn = wn * drn.spec;
+            DirL<T> dr;
+            dir_fwd_local(dr, px, pl, wx, wy, wz);
+            const T w = (T)tab.w[d] * wz;
+            const T ws = w * dr.spec;
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
                 const T e = x_exp2(lobe_arg(L.bx[k], L.by[k], L.bz[k], L.lam[k], wx, wy, wz));
                 U[k] += w * e;
                 V[k] += ws * e;
             }
-            w = wn;
-            ws = wsn;
         }
     } else {
         for (int d = 0; d < tab.D; ++d) {
@@ -130,14 +119,10 @@ IRB_HD void sweep_bwd(const Pixel<T>& px, const Lobes<T, KC>& L, const T (&P)[KC
         pixel_local_setup(pl, px);
         PixelGradL<T> gl;
         pixel_gradl_zero(gl);
-        DirL<T> dr;
-        dir_fwd_local(dr, px, pl, (T)tab.lx[0], (T)tab.ly[0], (T)tab.lz[0]);
         for (int d = 0; d < tab.D; ++d) {
             const T wx = (T)tab.lx[d], wy = (T)tab.ly[d], wz = (T)tab.lz[d];
-            // software pipeline: BRDF forward chain of direction d+1 overlaps the lobe chains of direction d
-            const int dn = d + 1 < tab.D ? d + 1 : d;
-            DirL<T> drn;
-            dir_fwd_local(drn, px, pl, (T)tab.lx[dn], (T)tab.ly[dn], (T)tab.lz[dn]);
+            DirL<T> dr;
+            dir_fwd_local(dr, px, pl, wx, wy, wz);
             const T w = (T)tab.w[d] * wz;
             T sQ = T(0);
 #pragma unroll
@@ -146,7 +131,6 @@ IRB_HD void sweep_bwd(const Pixel<T>& px, const Lobes<T, KC>& L, const T (&P)[KC
                 if (PIX) sQ += Q[k] * e;
             }
             if (PIX) dir_bwd_local(gl, px, pl, dr, wx, wy, wz, w * sQ);
-            dr = drn;
         }
         if (PIX) gradl_to_world(pg, gl, px);
     } else {

@@ -19,6 +19,7 @@
 // Fallback path (same math, same results): plain one-thread-per-pixel kernels with direct global
 // loads, used when a plane is not 16-byte addressable (R*C % 4 != 0 or misaligned base pointers).
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "irb_common.cuh"
 #include "irb_driver.cuh"
@@ -170,7 +171,11 @@ static int device_sms() {
     return sms > 0 ? sms : 148;
 }
 
+// test knobs (environment): IRB_DISABLE_TMA=1 forces the plain kernels; IRB_TMA_MAX_CTAS=n caps the persistent
+// grid so that small test problems still walk many tiles per CTA (exercises the 2-stage ring)
 static bool tma_ok(const RenderSgArgs& a, bool bwd) {
+    const char* dis = getenv("IRB_DISABLE_TMA");
+    if (dis && dis[0] == '1') return false;
     const size_t plane = (size_t)a.R * a.C;
     if (plane % 4 != 0) return false;
     const void* ptrs[] = {a.albedo, a.normal, a.rough, a.view, a.axis, a.lamb, a.weight, bwd ? a.g_diff : a.albedo,
@@ -200,6 +205,10 @@ static int launch_tma(KernelT kernel, const RenderSgArgs& a, const EnvTab& tab, 
     if (e != cudaSuccess || per_sm < 1) per_sm = 1;
     size_t grid = (size_t)device_sms() * per_sm;
     if (grid > total) grid = total;
+    if (const char* cap = getenv("IRB_TMA_MAX_CTAS")) {
+        const long c = atol(cap);
+        if (c > 0 && (size_t)c < grid) grid = (size_t)c;
+    }
     kernel<<<(unsigned)grid, kThreads, smem, st>>>(a, tab, (unsigned)total, (unsigned)tiles_per_img);
     return check_launch(what);
 }

@@ -216,3 +216,39 @@ def test_pool_matches_torch(irb):
         gx, = torch.autograd.grad(y, x, g)
         gxr, = torch.autograd.grad(yr, x, g)
         assert torch.allclose(gx, gxr, atol=1e-6)
+
+
+@pytest.mark.parametrize('cap', ['1', '3'])
+def test_tma_ring_many_tiles_per_cta(irb, cap, monkeypatch):
+    """persistent TMA kernels with the grid capped to 1 / 3 CTAs: every CTA walks many tiles through the
+    2-stage mbarrier ring (incl. a partial last tile); results must equal the plain kernels bit for bit and
+    match the fp64 oracle."""
+    from oracle import render_oracle as ro
+    B, R, C, K = 2, 30, 44, 12          # plane = 1320 = 10 full tiles + 40 px
+    ins64 = ro.synth_inputs(B, R, C, R, C, K, seed=777, dtype=torch.float64)
+    dev = torch.device('cuda')
+    g = torch.Generator().manual_seed(3)
+    gD = torch.rand(B, 3, R, C, generator=g).to(dev)
+    gS = torch.rand(B, 3, R, C, generator=g).to(dev)
+    rl = irb.renderingLayer(imWidth=C, imHeight=R, isCuda=True)
+
+    def run():
+        ins = [t.detach().float().to(dev).requires_grad_(True) for t in ins64]
+        d, s = rl.forwardSG(*ins)
+        gg = torch.autograd.grad([d, s], ins, [gD, gS])
+        torch.cuda.synchronize()
+        return [d.detach(), s.detach()] + [x.detach() for x in gg]
+    monkeypatch.setenv('IRB_DISABLE_TMA', '1')
+    plain = run()
+    monkeypatch.delenv('IRB_DISABLE_TMA')
+    monkeypatch.setenv('IRB_TMA_MAX_CTAS', cap)
+    tma = run()
+    monkeypatch.delenv('IRB_TMA_MAX_CTAS')
+    for a, b in zip(plain, tma):
+        assert torch.equal(a, b)
+    for t in ins64:
+        t.requires_grad_(True)
+    d64, s64 = ro.render_sg(*ins64)
+    g64 = torch.autograd.grad((d64 * gD.cpu().double()).sum() + (s64 * gS.cpu().double()).sum(), ins64)
+    for a, b in zip(tma, [d64, s64] + list(g64)):
+        assert relerr(a.cpu().numpy(), b.detach().numpy()) <= 2e-4
