@@ -121,7 +121,12 @@ __device__ __forceinline__ RenderSgArgs stage_view(const RenderSgArgs& a, float*
     return s;
 }
 
-// MODE 0: forward<KP>; MODE 1: backward<KP,KL,PIX,LOBE>
+}  // namespace irb
+#include "irb_render_sg_group.cuh"
+namespace irb {
+
+// MODE 0: forward<KP>; MODE 1: backward<KP,KL,PIX,LOBE>   (single-thread-per-pixel staged variant; kept for A/B via
+// IRB_RENDER_VARIANT=tma1)
 template <int MODE, int KP, int KL, bool PIX, bool LOBE>
 __global__ void __launch_bounds__(kThreads) render_sg_tma_kernel(const RenderSgArgs a, const __grid_constant__ EnvTab tab,
                                                                   const unsigned total_tiles, const unsigned tiles_per_img) {
@@ -186,15 +191,16 @@ static bool tma_ok(const RenderSgArgs& a, bool bwd) {
 }
 
 template <typename KernelT>
-static int launch_tma(KernelT kernel, const RenderSgArgs& a, const EnvTab& tab, bool bwd, cudaStream_t st, const char* what) {
+static int launch_tma(KernelT kernel, const RenderSgArgs& a, const EnvTab& tab, bool bwd, cudaStream_t st, const char* what,
+                      int tile = kTile) {
     const size_t plane = (size_t)a.R * a.C;
-    const size_t tiles_per_img = (plane + kTile - 1) / kTile;
+    const size_t tiles_per_img = (plane + tile - 1) / tile;
     const size_t total = tiles_per_img * (size_t)a.B;
     if (total >= 0xffffffffull) {
         set_error("%s: too many tiles", what);
         return IRB_E_UNSUPPORTED;
     }
-    const size_t smem = 2 * (size_t)stage_planes(a.K, bwd) * kTile * sizeof(float);
+    const size_t smem = 2 * (size_t)stage_planes(a.K, bwd) * tile * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", what, smem, cudaGetErrorString(e));
@@ -211,6 +217,15 @@ static int launch_tma(KernelT kernel, const RenderSgArgs& a, const EnvTab& tab, 
     }
     kernel<<<(unsigned)grid, kThreads, smem, st>>>(a, tab, (unsigned)total, (unsigned)tiles_per_img);
     return check_launch(what);
+}
+
+// IRB_RENDER_VARIANT = group (default: lobe-split persistent kernels + irregular-pixel follow-up), tma1, plain
+static int render_variant() {
+    const char* v = getenv("IRB_RENDER_VARIANT");
+    if (!v) return 0;
+    if (v[0] == 't') return 1;
+    if (v[0] == 'p') return 2;
+    return 0;
 }
 
 static int check_common(const RenderSgArgs& a, int envH, int envW, EnvTab& tab) {
@@ -247,9 +262,19 @@ extern "C" int irb_render_sg_fwd(const float* albedo, const float* normal, const
     if (int rc = check_common(a, envH, envW, tab)) return rc;
     IRB_REQUIRE(out_diff && out_spec, "render_sg_fwd: null output pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    if (tma_ok(a, false)) {
+    const int variant = tma_ok(a, false) ? render_variant() : 2;
+    if (variant == 1) {
         if (K <= 12) return launch_tma(render_sg_tma_kernel<0, 12, 12, false, false>, a, tab, false, st, "render_sg_fwd(tma)");
         return launch_tma(render_sg_tma_kernel<0, 24, 24, false, false>, a, tab, false, st, "render_sg_fwd(tma)");
+    }
+    if (variant == 0) {
+        int rc;
+        const char* w = "render_sg_fwd(group)";
+        if (K <= 6) rc = launch_tma(render_sg_group_kernel<0, 1, false, false, 4>, a, tab, false, st, w, kThreads / 1);
+        else if (K <= 12) rc = launch_tma(render_sg_group_kernel<0, 2, false, false, 4>, a, tab, false, st, w, kThreads / 2);
+        else rc = launch_tma(render_sg_group_kernel<0, 4, false, false, 4>, a, tab, false, st, w, kThreads / 4);
+        if (rc) return rc;
+        a.only_irregular = 1;  // follow-up: the clamped / degenerate pixels, general world-space path
     }
     const dim3 grid((unsigned)(((size_t)R * C + kThreads - 1) / kThreads), (unsigned)B);
     if (K <= 12) render_sg_fwd_kernel<12><<<grid, kThreads, 0, st>>>(a, tab);
@@ -274,7 +299,8 @@ extern "C" int irb_render_sg_bwd(const float* albedo, const float* normal, const
     const bool lobe = g_axis || g_lamb || g_weight || g_albedo;
     if (!pix && !lobe) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (tma_ok(a, true)) {
+    const int variant = tma_ok(a, true) ? render_variant() : 2;
+    if (variant == 1) {
         const char* w = "render_sg_bwd(tma)";
         if (K <= 12) {
             if (pix && lobe) return launch_tma(render_sg_tma_kernel<1, 12, 12, true, true>, a, tab, true, st, w);
@@ -284,6 +310,23 @@ extern "C" int irb_render_sg_bwd(const float* albedo, const float* normal, const
         if (pix && lobe) return launch_tma(render_sg_tma_kernel<1, 24, 12, true, true>, a, tab, true, st, w);
         if (pix) return launch_tma(render_sg_tma_kernel<1, 24, 12, true, false>, a, tab, true, st, w);
         return launch_tma(render_sg_tma_kernel<1, 24, 12, false, true>, a, tab, true, st, w);
+    }
+    if (variant == 0) {
+        int rc;
+        const char* w = "render_sg_bwd(group)";
+        const char* mb = getenv("IRB_BWD_MINB");  // A/B knob: 4 = cap the backward at 128 registers (spills) for 16 warps/SM
+        const bool minb4 = mb && mb[0] == '4';
+#define IRB_GROUP_BWD(TPP)                                                                                                   \
+    (pix && lobe ? (minb4 ? launch_tma(render_sg_group_kernel<1, TPP, true, true, 4>, a, tab, true, st, w, kThreads / TPP)    \
+                          : launch_tma(render_sg_group_kernel<1, TPP, true, true, 3>, a, tab, true, st, w, kThreads / TPP))   \
+     : pix      ? launch_tma(render_sg_group_kernel<1, TPP, true, false, 3>, a, tab, true, st, w, kThreads / TPP)            \
+                : launch_tma(render_sg_group_kernel<1, TPP, false, true, 3>, a, tab, true, st, w, kThreads / TPP))
+        if (K <= 6) rc = IRB_GROUP_BWD(1);
+        else if (K <= 12) rc = IRB_GROUP_BWD(2);
+        else rc = IRB_GROUP_BWD(4);
+#undef IRB_GROUP_BWD
+        if (rc) return rc;
+        a.only_irregular = 1;
     }
     const dim3 grid((unsigned)(((size_t)R * C + kThreads - 1) / kThreads), (unsigned)B);
     if (K <= 12) {

@@ -1,0 +1,301 @@
+// irb_render_sg_group.cuh -- LOBE-SPLIT persistent kernels of the fused SG render (device only).
+//
+// Why: with all K lobes of a pixel in one thread the backward needs ~250 registers, i.e. 2 warps per
+// scheduler, and ncu shows the sweep then stalls ~45 % of its issue slots on fixed-latency dependencies
+// (profiles/r01).  Here TPP = K/6 adjacent lanes share one pixel: each lane owns LPT = 6 lobes (72
+// accumulator/parameter registers instead of 144) and every TPP-th direction's BRDF chain, so the
+// register budget drops to <=128 (4 CTAs = 16 warps per SM) without duplicating any work:
+//   * direction d = m*TPP + j: lane j of the group evaluates dir_fwd_local / dir_bwd_local for it and
+//     broadcasts spec_d with one warp shuffle; every lane runs its 6 lobes for all directions;
+//   * the per-direction  sum_k Q_k e_kd  is completed across the group with a shuffle reduce-scatter;
+//   * per-pixel results (diffuse/spec, d/dnormal, d/drough, d/dalbedo) are butterfly-reduced once per pixel.
+// Same staging as irb_render_sg.cu: persistent CTAs, 2-stage cp.async.bulk + mbarrier ring, tile =
+// 128/TPP pixels.  Only pixels in the regular regime (irb_math.cuh) are handled here; the (rare)
+// clamped / degenerate ones are left to a follow-up launch of the plain kernel with only_irregular = 1,
+// which evaluates the general world-space path exactly as before.
+#pragma once
+
+namespace irb {
+
+template <int TPP> __device__ __forceinline__ float grp_allreduce(float v) {
+#pragma unroll
+    for (int o = 1; o < TPP; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// p[j] = this lane's partial for the direction owned by group member j; returns sum over members of p[h]
+template <int TPP> __device__ __forceinline__ float grp_reduce_scatter(const float (&p)[TPP], int h) {
+    if (TPP == 1) return p[0];
+    if (TPP == 2) {
+        const float send = h ? p[0] : p[1 % TPP];
+        const float keep = h ? p[1 % TPP] : p[0];
+        return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+    // TPP == 4
+    const bool hi = (h & 2) != 0;
+    const float a0 = (hi ? p[2 % TPP] : p[0]) + __shfl_xor_sync(0xffffffffu, hi ? p[0] : p[2 % TPP], 2);
+    const float a1 = (hi ? p[3 % TPP] : p[1 % TPP]) + __shfl_xor_sync(0xffffffffu, hi ? p[1 % TPP] : p[3 % TPP], 2);
+    const bool odd = (h & 1) != 0;
+    return (odd ? a1 : a0) + __shfl_xor_sync(0xffffffffu, odd ? a0 : a1, 1);
+}
+
+__device__ __forceinline__ void issue_tile_n(float* stage, uint64_t* bar, const RenderSgArgs& a, size_t tile, size_t tiles_per_img,
+                                             bool bwd, int PT) {
+    const int lane = threadIdx.x & 31;
+    const size_t plane = (size_t)a.R * a.C;
+    const size_t b = tile / tiles_per_img, pix0 = (tile % tiles_per_img) * (size_t)PT;
+    const uint32_t valid = (uint32_t)((plane - pix0) < (size_t)PT ? (plane - pix0) : (size_t)PT);
+    const uint32_t bytes = valid * 4u;
+    const int K = a.K;
+    const int np = stage_planes(K, bwd);
+    if (lane == 0) mbar_expect_tx(bar, bytes * (uint32_t)np);
+    __syncwarp();
+    for (int p = lane; p < np; p += 32) {
+        const float* src;
+        if (p < 3) src = a.albedo + (b * 3 + p) * plane;
+        else if (p < 6) src = a.normal + (b * 3 + (p - 3)) * plane;
+        else if (p < 7) src = a.rough + b * plane;
+        else if (p < 10) src = a.view + (size_t)(p - 7) * plane;
+        else if (p < 10 + 3 * K) src = a.axis + (b * 3 * K + (p - 10)) * plane;
+        else if (p < 10 + 4 * K) src = a.lamb + (b * K + (p - 10 - 3 * K)) * plane;
+        else if (p < 10 + 7 * K) src = a.weight + (b * 3 * K + (p - 10 - 4 * K)) * plane;
+        else if (p < 13 + 7 * K) src = a.g_diff + (b * 3 + (p - 10 - 7 * K)) * plane;
+        else src = a.g_spec + (b * 3 + (p - 13 - 7 * K)) * plane;
+        bulk_g2s(stage + (size_t)p * PT, src + pix0, bytes, bar);
+    }
+}
+
+__device__ __forceinline__ RenderSgArgs stage_view_n(const RenderSgArgs& a, float* stage, int PT) {
+    RenderSgArgs s = a;
+    const int K = a.K;
+    s.albedo = stage;
+    s.normal = stage + 3 * PT;
+    s.rough = stage + 6 * PT;
+    s.view = stage + 7 * PT;
+    s.axis = stage + 10 * PT;
+    s.lamb = stage + (10 + 3 * K) * PT;
+    s.weight = stage + (10 + 4 * K) * PT;
+    s.g_diff = stage + (10 + 7 * K) * PT;
+    s.g_spec = stage + (13 + 7 * K) * PT;
+    return s;
+}
+
+// hemisphere table in shared memory (the BRDF direction index differs between the lanes of a group)
+struct TabS {
+    float lx[IRB_MAX_DIRS], ly[IRB_MAX_DIRS], lz[IRB_MAX_DIRS], w[IRB_MAX_DIRS];
+};
+
+constexpr int kLPT = 6;
+
+// ---- one tile, forward ----------------------------------------------------------------------
+template <int TPP>
+__device__ __forceinline__ void group_tile_fwd(const RenderSgArgs& a, const RenderSgArgs& sv, const EnvTab& tab, const TabS& ts,
+                                               const PixView& vi, const PixView& vo, bool in_range, int h) {
+    const int lane = threadIdx.x & 31, lane_base = lane - h;
+    Pixel<float> px;
+    V3<float> nt;
+    float A[3];
+    load_pixel(px, nt, A, sv, vi.b, vi.pix, vi.plane);
+    const bool active = in_range && px.regular;
+    PixelLocal<float> pl;
+    pixel_local_setup(pl, px);
+    Lobes<float, kLPT> L;
+    load_lobes(L, sv, vi.b, vi.pix, vi.plane, h * kLPT);
+    float U[kLPT], V[kLPT];
+#pragma unroll
+    for (int k = 0; k < kLPT; ++k) U[k] = V[k] = 0.f;
+    for (int m = 0; m < tab.D; m += TPP) {
+        const int dm = m + h;
+        DirL<float> dr;
+        dir_fwd_local(dr, px, pl, ts.lx[dm], ts.ly[dm], ts.lz[dm]);
+#pragma unroll
+        for (int j = 0; j < TPP; ++j) {
+            const int d = m + j;
+            const float wx = tab.lx[d], wy = tab.ly[d], wz = tab.lz[d];
+            const float spec = __shfl_sync(0xffffffffu, dr.spec, lane_base + j);
+            const float w = tab.w[d] * wz;
+            const float ws = w * spec;
+#pragma unroll
+            for (int k = 0; k < kLPT; ++k) {
+                const float e = x_exp2(lobe_arg(L.bx[k], L.by[k], L.bz[k], L.lam[k], wx, wy, wz));
+                U[k] += w * e;
+                V[k] += ws * e;
+            }
+        }
+    }
+    float Dc[3] = {0.f, 0.f, 0.f}, Sc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < kLPT; ++k) {
+        if (h * kLPT + k < sv.K) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float w = load_weight<float>(sv, vi.b, vi.pix, vi.plane, h * kLPT + k, c);
+                Dc[c] += w * U[k];
+                Sc[c] += w * V[k];
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        Dc[c] = grp_allreduce<TPP>(Dc[c]);
+        Sc[c] = grp_allreduce<TPP>(Sc[c]);
+    }
+    if (active && h == 0) {
+        const size_t o3 = (vo.b * 3) * vo.plane + vo.pix;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            a.out_diff[o3 + c * vo.plane] = A[c] * Consts<float>::INV_PI * Dc[c];
+            a.out_spec[o3 + c * vo.plane] = Sc[c];
+        }
+    }
+}
+
+// ---- one tile, backward ---------------------------------------------------------------------
+template <int TPP, bool PIX, bool LOBE>
+__device__ __forceinline__ void group_tile_bwd(const RenderSgArgs& a, const RenderSgArgs& sv, const EnvTab& tab, const TabS& ts,
+                                               const PixView& vi, const PixView& vo, bool in_range, int h) {
+    const int lane = threadIdx.x & 31, lane_base = lane - h;
+    const size_t i3 = (vi.b * 3) * vi.plane + vi.pix;
+    float gD[3], gS[3], gDa[3];
+    bool active;
+    PixelGradL<float> gl;
+    pixel_gradl_zero(gl);
+    LobeGrads<float, kLPT> lg;
+    Lobes<float, kLPT> L;
+    float P[kLPT], Q[kLPT];
+    {
+        Pixel<float> px;
+        V3<float> nt;
+        float A[3];
+        load_pixel(px, nt, A, sv, vi.b, vi.pix, vi.plane);
+        active = in_range && px.regular;
+        PixelLocal<float> pl;
+        pixel_local_setup(pl, px);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            gD[c] = sv.g_diff[i3 + c * vi.plane];
+            gS[c] = sv.g_spec[i3 + c * vi.plane];
+            gDa[c] = gD[c] * A[c] * Consts<float>::INV_PI;
+        }
+        load_lobes(L, sv, vi.b, vi.pix, vi.plane, h * kLPT);
+        load_PQ<float, kLPT>(P, Q, sv, vi.b, vi.pix, vi.plane, h * kLPT, gDa, gS);
+#pragma unroll
+        for (int k = 0; k < kLPT; ++k) lg.U[k] = lg.V[k] = lg.S[k] = lg.mx[k] = lg.my[k] = lg.mz[k] = 0.f;
+        for (int m = 0; m < tab.D; m += TPP) {
+            const int dm = m + h;
+            const float wxm = ts.lx[dm], wym = ts.ly[dm], wzm = ts.lz[dm];
+            DirL<float> dr;
+            dir_fwd_local(dr, px, pl, wxm, wym, wzm);
+            float part[TPP];
+#pragma unroll
+            for (int j = 0; j < TPP; ++j) {
+                const int d = m + j;
+                const float wx = tab.lx[d], wy = tab.ly[d], wz = tab.lz[d];
+                const float spec = __shfl_sync(0xffffffffu, dr.spec, lane_base + j);
+                const float w = tab.w[d] * wz;
+                float sQ = 0.f;
+#pragma unroll
+                for (int k = 0; k < kLPT; ++k) {
+                    const float e = lobe_bwd_body<float, kLPT, LOBE>(lg, L, P, Q, k, wx, wy, wz, w, spec);
+                    if (PIX) sQ += Q[k] * e;
+                }
+                part[j] = sQ;
+            }
+            if (PIX) {
+                const float sQm = grp_reduce_scatter<TPP>(part, h);
+                dir_bwd_local(gl, px, pl, dr, wxm, wym, wzm, ts.w[dm] * wzm * sQm);
+            }
+        }
+    }
+    // epilogue: outputs are predicated per thread by nulling the pointers of inactive threads
+    RenderSgArgs ao = a;
+    if (!active) ao.g_axis = ao.g_lamb = ao.g_weight = nullptr;
+    float gAlb[3] = {0.f, 0.f, 0.f};
+    if (LOBE) store_lobe_grads<float, kLPT>(lg, L, P, Q, sv, vi, ao, vo, h * kLPT, gDa, gS, gAlb);
+    const size_t o3 = (vo.b * 3) * vo.plane + vo.pix;
+    if (LOBE && a.g_albedo) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gAlb[c] = grp_allreduce<TPP>(gAlb[c]);
+        if (active && h == 0) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) a.g_albedo[o3 + c * vo.plane] = gD[c] * Consts<float>::INV_PI * gAlb[c];
+        }
+    }
+    if (PIX) {
+        gl.Gxx = grp_allreduce<TPP>(gl.Gxx); gl.Gxy = grp_allreduce<TPP>(gl.Gxy); gl.Gxz = grp_allreduce<TPP>(gl.Gxz);
+        gl.Gyx = grp_allreduce<TPP>(gl.Gyx); gl.Gyy = grp_allreduce<TPP>(gl.Gyy); gl.Gyz = grp_allreduce<TPP>(gl.Gyz);
+        gl.Gzx = grp_allreduce<TPP>(gl.Gzx); gl.Gzy = grp_allreduce<TPP>(gl.Gzy); gl.Gzz = grp_allreduce<TPP>(gl.Gzz);
+        gl.gnx = grp_allreduce<TPP>(gl.gnx); gl.gny = grp_allreduce<TPP>(gl.gny); gl.gnz = grp_allreduce<TPP>(gl.gnz);
+        gl.G_n1 = grp_allreduce<TPP>(gl.G_n1);
+        gl.g_alpha2 = grp_allreduce<TPP>(gl.g_alpha2);
+        gl.g_k = grp_allreduce<TPP>(gl.g_k);
+        if (active && h == 0) {
+            // the world-space pixel state is recomputed here instead of being kept alive through the sweep
+            Pixel<float> px;
+            V3<float> nt;
+            float A[3];
+            load_pixel(px, nt, A, sv, vi.b, vi.pix, vi.plane);
+            PixelGrad<float> pg;
+            gradl_to_world(pg, gl, px);
+            V3<float> g_nt;
+            float g_rough;
+            pixel_bwd_finish(pg, px, nt, g_nt, g_rough);
+            if (a.g_normal) {
+                a.g_normal[o3] = g_nt.x;
+                a.g_normal[o3 + vo.plane] = g_nt.y;
+                a.g_normal[o3 + 2 * vo.plane] = g_nt.z;
+            }
+            if (a.g_rough) a.g_rough[vo.b * vo.plane + vo.pix] = g_rough;
+        }
+    }
+}
+
+// MODE 0 forward, 1 backward
+template <int MODE, int TPP, bool PIX, bool LOBE, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) render_sg_group_kernel(const RenderSgArgs a, const __grid_constant__ EnvTab tab,
+                                                                          const unsigned total_tiles, const unsigned tiles_per_img) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[2];
+    __shared__ TabS ts;
+    constexpr bool BWD = (MODE == 1);
+    constexpr int PT = kThreads / TPP;
+    const int np = stage_planes(a.K, BWD);
+    float* const stage0 = reinterpret_cast<float*>(smem_raw);
+    float* const stage1 = stage0 + (size_t)np * PT;
+    for (int i = threadIdx.x; i < IRB_MAX_DIRS; i += kThreads) {
+        ts.lx[i] = tab.lx[i];
+        ts.ly[i] = tab.ly[i];
+        ts.lz[i] = tab.lz[i];
+        ts.w[i] = tab.w[i];
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(&full_bar[0], 1);
+        mbar_init(&full_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const size_t plane = (size_t)a.R * a.C;
+    const int q = threadIdx.x / TPP, h = threadIdx.x % TPP;
+    unsigned t = blockIdx.x;
+    if (t < total_tiles && threadIdx.x < 32) issue_tile_n(stage0, &full_bar[0], a, t, tiles_per_img, BWD, PT);
+    for (unsigned it = 0; t < total_tiles; ++it, t += gridDim.x) {
+        const int s = it & 1;
+        float* const cur = s ? stage1 : stage0;
+        const unsigned tn = t + gridDim.x;
+        if (tn < total_tiles && threadIdx.x < 32) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue_tile_n(s ? stage0 : stage1, &full_bar[s ^ 1], a, tn, tiles_per_img, BWD, PT);
+        }
+        mbar_wait(&full_bar[s], (it >> 1) & 1);
+        const size_t b = t / tiles_per_img, pix0 = (size_t)(t % tiles_per_img) * PT;
+        const bool in_range = pix0 + q < plane;
+        const RenderSgArgs sv = stage_view_n(a, cur, PT);
+        const PixView vi{0, (size_t)q, (size_t)PT};
+        const PixView vo{b, pix0 + q, plane};
+        if (MODE == 0) group_tile_fwd<TPP>(a, sv, tab, ts, vi, vo, in_range, h);
+        else group_tile_bwd<TPP, PIX, LOBE>(a, sv, tab, ts, vi, vo, in_range, h);
+        __syncthreads();
+    }
+}
+
+}  // namespace irb
