@@ -133,7 +133,7 @@ template <> IRB_HD float sg_warp<float>(float x) {
     t = fmaf(-c_lo, x, t);                                       // 1 - 0.999 x, single rounding of the exact value
     const bool low = a <= 0.5f;
     const float tz = tan_q(HALF_PI * (low ? a : t));
-    return low ? tz : 1.0f / tz;
+    return low ? tz : x_rcp(tz);   // rcp.approx: <= 1 ulp, no IEEE-division slow path
 }
 // d tan(c x)/dx = c (1 + tan^2)
 template <typename T> IRB_HD T sg_warp_grad(T y) {
@@ -371,15 +371,11 @@ template <typename T> IRB_HD void dir_fwd_local(DirL<T>& dr, const Pixel<T>& px,
     dr.F = px.F0 + (T(1) - px.F0) * dr.p2;
     dr.ndh_raw = dr.Mz * dr.rinv;
     dr.ndh = x_clamp(dr.ndh_raw, T(0), T(1));
-    if (dr.ndh_raw <= T(0)) {
-        dr.n0 = T(1);
-    } else if (dr.ndh_raw >= T(1)) {
-        dr.n0 = px.alpha2;
-    } else if (dr.mm_ok) {
-        dr.n0 = q * dr.rinv * dr.rinv + px.alpha2 * dr.ndh * dr.ndh;   // 1 - ndh^2 = (Mx^2+My^2)/|M|^2
-    } else {
-        dr.n0 = dr.ndh * dr.ndh * (px.alpha2 - T(1)) + T(1);
-    }
+    // branch-free: 1 - ndh^2 = (Mx^2+My^2)/|M|^2 (no cancellation); under the m.m clamp |h| < 1 and the
+    // literal form is used; the ndh clamps give n0 = 1 / alpha2 exactly
+    const T a2n = px.alpha2 * dr.ndh * dr.ndh;
+    const T n0_reg = dr.mm_ok ? (q * dr.rinv * dr.rinv + a2n) : (a2n - dr.ndh * dr.ndh + T(1));
+    dr.n0 = dr.ndh_raw <= T(0) ? T(1) : (dr.ndh_raw >= T(1) ? px.alpha2 : n0_reg);
     dr.n2 = wz * (T(1) - px.k) + px.k;        // ndl = l.z
     dr.nom_raw = Consts<T>::FOUR_PI * dr.n0 * dr.n0 * px.n1 * dr.n2;
     dr.inv_nom = x_rcp(x_clamp(dr.nom_raw, (T)1e-6, Consts<T>::FOUR_PI));

@@ -39,6 +39,17 @@ template <typename T> IRB_HD T lobe_arg(T bx, T by, T bz, T lam, T wx, T wy, T w
     return bx * wx + (by * wy + (bz * wz - lam));
 }
 
+// All KC exponentials of one direction, written in three explicit phases (arguments, SFU, uses) so that the
+// KC independent chains are in flight together instead of one fma->fma->fma->ex2->use chain after the other
+// (ncu: the dependent multiply right behind each MUFU.EX2 was the top short-scoreboard stall).
+template <typename T, int KC>
+IRB_HD void lobe_exps(const Lobes<T, KC>& L, T wx, T wy, T wz, T (&arg)[KC], T (&e)[KC]) {
+#pragma unroll
+    for (int k = 0; k < KC; ++k) arg[k] = lobe_arg(L.bx[k], L.by[k], L.bz[k], L.lam[k], wx, wy, wz);
+#pragma unroll
+    for (int k = 0; k < KC; ++k) e[k] = x_exp2(arg[k]);
+}
+
 template <typename T, int KC>
 IRB_HD void sweep_fwd(const Pixel<T>& px, const Lobes<T, KC>& L, const EnvTab& tab, T (&U)[KC], T (&V)[KC]) {
 #pragma unroll
@@ -56,11 +67,12 @@ IRB_HD void sweep_fwd(const Pixel<T>& px, const Lobes<T, KC>& L, const EnvTab& t
             dir_fwd_local(dr, px, pl, wx, wy, wz);
             const T w = (T)tab.w[d] * wz;
             const T ws = w * dr.spec;
+            T arg[KC], e[KC];
+            lobe_exps<T, KC>(L, wx, wy, wz, arg, e);
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
-                const T e = x_exp2(lobe_arg(L.bx[k], L.by[k], L.bz[k], L.lam[k], wx, wy, wz));
-                U[k] += w * e;
-                V[k] += ws * e;
+                U[k] += w * e[k];
+                V[k] += ws * e[k];
             }
         }
     } else {
@@ -70,11 +82,12 @@ IRB_HD void sweep_fwd(const Pixel<T>& px, const Lobes<T, KC>& L, const EnvTab& t
             dir_fwd(dr, px, wx, wy, wz);
             const T w = (T)tab.w[d] * dr.ndl;
             const T ws = w * dr.spec;
+            T arg[KC], e[KC];
+            lobe_exps<T, KC>(L, wx, wy, wz, arg, e);
 #pragma unroll
             for (int k = 0; k < KC; ++k) {
-                const T e = x_exp2(lobe_arg(L.bx[k], L.by[k], L.bz[k], L.lam[k], wx, wy, wz));
-                U[k] += w * e;
-                V[k] += ws * e;
+                U[k] += w * e[k];
+                V[k] += ws * e[k];
             }
         }
     }
@@ -84,23 +97,32 @@ template <typename T, int KC> struct LobeGrads {
     T U[KC], V[KC], S[KC], mx[KC], my[KC], mz[KC];  // S = sum T arg ; m = sum T w_d
 };
 
-// per-(direction, lobe) body of the backward sweep; returns e
-template <typename T, int KC, bool LOBE>
-IRB_HD T lobe_bwd_body(LobeGrads<T, KC>& lg, const Lobes<T, KC>& L, const T (&P)[KC], const T (&Q)[KC], int k, T wx, T wy, T wz,
-                       T w, T spec) {
-    const T arg = lobe_arg(L.bx[k], L.by[k], L.bz[k], L.lam[k], wx, wy, wz);
-    const T e = x_exp2(arg);
-    if (LOBE) {
-        const T ew = e * w;
-        lg.U[k] += ew;
-        lg.V[k] += ew * spec;
-        const T t = ew * (P[k] + spec * Q[k]);
-        lg.S[k] += t * arg;
-        lg.mx[k] += t * wx;
-        lg.my[k] += t * wy;
-        lg.mz[k] += t * wz;
+// lobe part of one direction of the backward sweep; returns sum_k Q_k e_kd
+template <typename T, int KC, bool PIX, bool LOBE>
+IRB_HD T lobes_bwd_dir(LobeGrads<T, KC>& lg, const Lobes<T, KC>& L, const T (&P)[KC], const T (&Q)[KC], T wx, T wy, T wz, T w,
+                       T spec, T& sP) {
+    T arg[KC], e[KC];
+    lobe_exps<T, KC>(L, wx, wy, wz, arg, e);
+    T sQ = T(0);
+    sP = T(0);
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        if (PIX) {
+            sQ += Q[k] * e[k];
+            sP += P[k] * e[k];
+        }
+        if (LOBE) {
+            const T ew = e[k] * w;
+            lg.U[k] += ew;
+            lg.V[k] += ew * spec;
+            const T t = ew * (P[k] + spec * Q[k]);
+            lg.S[k] += t * arg[k];
+            lg.mx[k] += t * wx;
+            lg.my[k] += t * wy;
+            lg.mz[k] += t * wz;
+        }
     }
-    return e;
+    return sQ;
 }
 
 // One backward sweep.  PIX: accumulate the BRDF-side gradients (needs ALL lobes of the pixel in
@@ -124,12 +146,8 @@ IRB_HD void sweep_bwd(const Pixel<T>& px, const Lobes<T, KC>& L, const T (&P)[KC
             DirL<T> dr;
             dir_fwd_local(dr, px, pl, wx, wy, wz);
             const T w = (T)tab.w[d] * wz;
-            T sQ = T(0);
-#pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                const T e = lobe_bwd_body<T, KC, LOBE>(lg, L, P, Q, k, wx, wy, wz, w, dr.spec);
-                if (PIX) sQ += Q[k] * e;
-            }
+            T sP;
+            const T sQ = lobes_bwd_dir<T, KC, PIX, LOBE>(lg, L, P, Q, wx, wy, wz, w, dr.spec, sP);
             if (PIX) dir_bwd_local(gl, px, pl, dr, wx, wy, wz, w * sQ);
         }
         if (PIX) gradl_to_world(pg, gl, px);
@@ -140,15 +158,8 @@ IRB_HD void sweep_bwd(const Pixel<T>& px, const Lobes<T, KC>& L, const T (&P)[KC
             dir_fwd(dr, px, wx, wy, wz);
             const T om = (T)tab.w[d];
             const T w = om * dr.ndl;
-            T eD = T(0), eS = T(0);
-#pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                const T e = lobe_bwd_body<T, KC, LOBE>(lg, L, P, Q, k, wx, wy, wz, w, dr.spec);
-                if (PIX) {
-                    eD += P[k] * e;
-                    eS += Q[k] * e;
-                }
-            }
+            T eD;
+            const T eS = lobes_bwd_dir<T, KC, PIX, LOBE>(lg, L, P, Q, wx, wy, wz, w, dr.spec, eD);
             if (PIX) dir_bwd(pg, px, dr, wx, wy, wz, om * eD, om * eS);
         }
     }

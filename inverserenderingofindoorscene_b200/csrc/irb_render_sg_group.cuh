@@ -115,11 +115,12 @@ __device__ __forceinline__ void group_tile_fwd(const RenderSgArgs& a, const Rend
             const float spec = __shfl_sync(0xffffffffu, dr.spec, lane_base + j);
             const float w = tab.w[d] * wz;
             const float ws = w * spec;
+            float arg[kLPT], e[kLPT];
+            lobe_exps<float, kLPT>(L, wx, wy, wz, arg, e);
 #pragma unroll
             for (int k = 0; k < kLPT; ++k) {
-                const float e = x_exp2(lobe_arg(L.bx[k], L.by[k], L.bz[k], L.lam[k], wx, wy, wz));
-                U[k] += w * e;
-                V[k] += ws * e;
+                U[k] += w * e[k];
+                V[k] += ws * e[k];
             }
         }
     }
@@ -193,13 +194,8 @@ __device__ __forceinline__ void group_tile_bwd(const RenderSgArgs& a, const Rend
                 const float wx = tab.lx[d], wy = tab.ly[d], wz = tab.lz[d];
                 const float spec = __shfl_sync(0xffffffffu, dr.spec, lane_base + j);
                 const float w = tab.w[d] * wz;
-                float sQ = 0.f;
-#pragma unroll
-                for (int k = 0; k < kLPT; ++k) {
-                    const float e = lobe_bwd_body<float, kLPT, LOBE>(lg, L, P, Q, k, wx, wy, wz, w, spec);
-                    if (PIX) sQ += Q[k] * e;
-                }
-                part[j] = sQ;
+                float sP_unused;
+                part[j] = lobes_bwd_dir<float, kLPT, PIX, LOBE>(lg, L, P, Q, wx, wy, wz, w, spec, sP_unused);
             }
             if (PIX) {
                 const float sQm = grp_reduce_scatter<TPP>(part, h);
