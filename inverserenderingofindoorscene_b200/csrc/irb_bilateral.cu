@@ -20,13 +20,11 @@ namespace irb {
 constexpr int BG_DIM = 5;
 constexpr int BG_MAX_ITERS = 256;
 constexpr int BG_MAX_CH = 4;
-constexpr int SORT_THREADS = 1024;
-constexpr int SORT_WARPS = SORT_THREADS / 32;
 
 struct BgLayout {
     int B, H, W, ch;
     size_t P;
-    size_t hdr, idx, vstart, ukeys, nbr, n0, n1, m, m0, keysA, keysB, payA, payB;
+    size_t hdr, idx, vstart, ukeys, nbr, n0, n1, m, m0, keysA, keysB, payA, payB, hist;
     size_t wsplat, minv, bvec, r, p0, p1, q, sol, scal, total;
 };
 
@@ -52,6 +50,7 @@ static BgLayout make_layout(int B, int H, int W, int ch) {
     L.keysB = take(8 * P * Bz);
     L.payA = take(4 * P * Bz);
     L.payB = take(4 * P * Bz);
+    L.hist = take(4 * 256 * (size_t)256 * Bz);  // radix-sort bucket counters [img][digit][warp-chunk]
     L.wsplat = take(8 * P * Bz);
     L.minv = take(8 * P * Bz);
     const size_t vc = 8 * P * Bz * (size_t)(ch > 0 ? ch : 1);
@@ -97,138 +96,179 @@ __global__ void bg_keys_kernel(const float* __restrict__ guide, float gscale, vo
 }
 
 // ---------------------------------------------------------------------------------------------
-// 2. one CTA per image: stable LSD radix sort of (hash, pixel) on 8-bit digits, then
-//    unique -> vertex ids (np.unique, BilateralGrid.py:64-65)
+// 2. stable LSD radix sort of (hash, pixel) on 8-bit digits, all images per launch, then
+//    unique -> vertex ids (np.unique, BilateralGrid.py:64-65).
+//    Each image is cut into SORT_WPI warp-chunks of consecutive elements; per pass:
+//      hist    : every warp counts the digits of its chunk            -> hist[img][digit][warp]
+//      scan    : one CTA per image, exclusive scan in (digit, warp) order (stable bucket offsets)
+//      scatter : every warp re-reads its chunk in order, ranks equal digits inside each group of
+//                32 keys with __match_any_sync and writes (key, pixel) to its private bucket cursor
+//    (the first version ran the whole sort in ONE 1024-thread CTA per image: 3.2 ms; profiles/r01)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SORT_THREADS) bg_sort_unique_kernel(void* ws, BgLayout L, int npass) {
-    __shared__ unsigned hist[256 * SORT_WARPS];
-    __shared__ unsigned wtot[SORT_WARPS];
-    __shared__ unsigned carry_s;
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t P = L.P;
-    unsigned long long* kA = at<unsigned long long>(ws, L.keysA) + (size_t)b * P;
-    unsigned long long* kB = at<unsigned long long>(ws, L.keysB) + (size_t)b * P;
-    int* pA = at<int>(ws, L.payA) + (size_t)b * P;
-    int* pB = at<int>(ws, L.payB) + (size_t)b * P;
-    const size_t chunk = (P + SORT_WARPS - 1) / SORT_WARPS;
+constexpr int SORT_WPI = 256;        // warp-chunks per image
+constexpr int SORT_CTA_WARPS = 8;    // warps per CTA in hist / scatter / unique kernels
+
+struct SortIO {
+    const unsigned long long* kin;
+    const int* pin;
+    unsigned long long* kout;
+    int* pout;
+};
+
+__device__ __forceinline__ SortIO sort_io(void* ws, const BgLayout& L, int b, int pass) {
+    const size_t o = (size_t)b * L.P;
+    unsigned long long* kA = at<unsigned long long>(ws, L.keysA) + o;
+    unsigned long long* kB = at<unsigned long long>(ws, L.keysB) + o;
+    int* pA = at<int>(ws, L.payA) + o;
+    int* pB = at<int>(ws, L.payB) + o;
+    return (pass & 1) ? SortIO{kB, pB, kA, pA} : SortIO{kA, pA, kB, pB};
+}
+
+__global__ void __launch_bounds__(SORT_CTA_WARPS * 32) bg_sort_hist_kernel(void* ws, BgLayout L, int pass) {
+    __shared__ unsigned sh[SORT_CTA_WARPS][256];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int warp = blockIdx.x * SORT_CTA_WARPS + wl;  // chunk id inside the image
+    const size_t P = L.P, chunk = (P + SORT_WPI - 1) / SORT_WPI;
     const size_t beg = (size_t)warp * chunk, end = beg + chunk < P ? beg + chunk : P;
-    for (int pass = 0; pass < npass; ++pass) {
-        const int shift = 8 * pass;
-        for (int i = tid; i < 256 * SORT_WARPS; i += SORT_THREADS) hist[i] = 0;
-        __syncthreads();
-        // count
-        for (size_t i = beg; i < end; i += 32) {
-            const bool ok = i + lane < end;
-            const unsigned valid = __ballot_sync(0xffffffffu, ok);
-            if (ok) {
-                const unsigned d = (unsigned)(kA[i + lane] >> shift) & 255u;
-                const unsigned peers = __match_any_sync(valid, d);
-                if (lane == __ffs(peers) - 1) hist[d * SORT_WARPS + warp] += __popc(peers);
-            }
-        }
-        __syncthreads();
-        // exclusive scan over (digit major, warp minor): 8192 entries, 8 per thread
-        {
-            unsigned loc[8], s = 0;
+    const SortIO io = sort_io(ws, L, b, pass);
+    const int shift = 8 * pass;
+    for (int i = lane; i < 256; i += 32) sh[wl][i] = 0;
+    __syncwarp();
+    for (size_t i = beg + lane; i < end; i += 32) atomicAdd(&sh[wl][(unsigned)(io.kin[i] >> shift) & 255u], 1u);
+    __syncwarp();
+    unsigned* hist = at<unsigned>(ws, L.hist) + (size_t)b * 256 * SORT_WPI;
+    for (int d = lane; d < 256; d += 32) hist[(size_t)d * SORT_WPI + warp] = sh[wl][d];
+}
+
+__global__ void __launch_bounds__(1024) bg_sort_scan_kernel(void* ws, BgLayout L) {
+    __shared__ unsigned wtot[32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned* hist = at<unsigned>(ws, L.hist) + (size_t)b * 256 * SORT_WPI;
+    constexpr int PER = 256 * SORT_WPI / 1024;  // consecutive entries per thread
+    unsigned loc[PER], s = 0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                loc[j] = hist[tid * 8 + j];
-                s += loc[j];
-            }
-            unsigned inc = s;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += v;
-            }
-            if (lane == 31) wtot[warp] = inc;
-            __syncthreads();
-            if (warp == 0) {
-                unsigned v = wtot[lane], iv = v;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned u = __shfl_up_sync(0xffffffffu, iv, o);
-                    if (lane >= o) iv += u;
-                }
-                wtot[lane] = iv - v;
-            }
-            __syncthreads();
-            unsigned run = wtot[warp] + inc - s;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                hist[tid * 8 + j] = run;
-                run += loc[j];
-            }
-        }
-        __syncthreads();
-        // stable scatter
-        for (size_t i = beg; i < end; i += 32) {
-            const bool ok = i + lane < end;
-            const unsigned valid = __ballot_sync(0xffffffffu, ok);
-            if (ok) {
-                const unsigned long long key = kA[i + lane];
-                const int pay = pA[i + lane];
-                const unsigned d = (unsigned)(key >> shift) & 255u;
-                const unsigned peers = __match_any_sync(valid, d);
-                const unsigned base = hist[d * SORT_WARPS + warp];
-                const unsigned rank = __popc(peers & ((1u << lane) - 1u));
-                __syncwarp(valid);
-                if (lane == __ffs(peers) - 1) hist[d * SORT_WARPS + warp] = base + __popc(peers);
-                kB[base + rank] = key;
-                pB[base + rank] = pay;
-            }
-            __syncwarp();
-        }
-        __syncthreads();
-        unsigned long long* tk = kA; kA = kB; kB = tk;
-        int* tp = pA; pA = pB; pB = tp;
+    for (int j = 0; j < PER; ++j) {
+        loc[j] = hist[(size_t)tid * PER + j];
+        s += loc[j];
     }
-    // sorted data is now in kA / pA.  unique + rank.
+    unsigned inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned v = wtot[lane];
+        unsigned iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned u = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= o) iv += u;
+        }
+        wtot[lane] = iv - v;
+    }
+    __syncthreads();
+    unsigned run = wtot[warp] + inc - s;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        hist[(size_t)tid * PER + j] = run;
+        run += loc[j];
+    }
+}
+
+__global__ void __launch_bounds__(SORT_CTA_WARPS * 32) bg_sort_scatter_kernel(void* ws, BgLayout L, int pass) {
+    __shared__ unsigned cur[SORT_CTA_WARPS][256];
+    const int b = blockIdx.y, lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int warp = blockIdx.x * SORT_CTA_WARPS + wl;
+    const size_t P = L.P, chunk = (P + SORT_WPI - 1) / SORT_WPI;
+    const size_t beg = (size_t)warp * chunk, end = beg + chunk < P ? beg + chunk : P;
+    const SortIO io = sort_io(ws, L, b, pass);
+    const int shift = 8 * pass;
+    const unsigned* hist = at<unsigned>(ws, L.hist) + (size_t)b * 256 * SORT_WPI;
+    for (int d = lane; d < 256; d += 32) cur[wl][d] = hist[(size_t)d * SORT_WPI + warp];
+    __syncwarp();
+    for (size_t i = beg; i < end; i += 32) {
+        const bool ok = i + lane < end;
+        const unsigned valid = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const unsigned long long key = io.kin[i + lane];
+            const int pay = io.pin[i + lane];
+            const unsigned d = (unsigned)(key >> shift) & 255u;
+            const unsigned peers = __match_any_sync(valid, d);
+            const unsigned base = cur[wl][d];
+            const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+            __syncwarp(valid);
+            if (lane == __ffs(peers) - 1) cur[wl][d] = base + __popc(peers);
+            io.kout[base + rank] = key;
+            io.pout[base + rank] = pay;
+        }
+        __syncwarp();
+    }
+}
+
+// unique, phase 1: number of distinct-key heads in every warp-chunk (sorted data in keysB / payB)
+__global__ void __launch_bounds__(SORT_CTA_WARPS * 32) bg_unique_count_kernel(void* ws, BgLayout L) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int warp = blockIdx.x * SORT_CTA_WARPS + wl;
+    const size_t P = L.P, chunk = (P + SORT_WPI - 1) / SORT_WPI;
+    const size_t beg = (size_t)warp * chunk, end = beg + chunk < P ? beg + chunk : P;
+    const unsigned long long* k = at<unsigned long long>(ws, L.keysB) + (size_t)b * P;
+    unsigned cnt = 0;
+    for (size_t i = beg + lane; i < end; i += 32) cnt += (i == 0 || k[i - 1] != k[i]) ? 1u : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    if (lane == 0) at<unsigned>(ws, L.hist)[(size_t)b * 256 * SORT_WPI + warp] = cnt;
+}
+
+// unique, phase 2: vertex id = rank of the key among the sorted unique keys
+__global__ void __launch_bounds__(SORT_CTA_WARPS * 32) bg_unique_rank_kernel(void* ws, BgLayout L) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int warp = blockIdx.x * SORT_CTA_WARPS + wl;
+    const size_t P = L.P, chunk = (P + SORT_WPI - 1) / SORT_WPI;
+    const size_t beg = (size_t)warp * chunk, end = beg + chunk < P ? beg + chunk : P;
+    const unsigned long long* k = at<unsigned long long>(ws, L.keysB) + (size_t)b * P;
+    const int* sp = at<int>(ws, L.payB) + (size_t)b * P;
+    const unsigned* cnts = at<unsigned>(ws, L.hist) + (size_t)b * 256 * SORT_WPI;
+    // heads in the chunks before mine (and, for the last warp, the image total)
+    unsigned before = 0, total = 0;
+    for (int w = lane; w < SORT_WPI; w += 32) {
+        const unsigned c = cnts[w];
+        total += c;
+        if (w < warp) before += c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        before += __shfl_xor_sync(0xffffffffu, before, o);
+        total += __shfl_xor_sync(0xffffffffu, total, o);
+    }
     int* idx = at<int>(ws, L.idx) + (size_t)b * P;
     int* vstart = at<int>(ws, L.vstart) + (size_t)b * (P + 1);
     unsigned long long* ukeys = at<unsigned long long>(ws, L.ukeys) + (size_t)b * P;
-    int* sp = at<int>(ws, L.payB) + (size_t)b * P;  // final sorted pixel list always lands in payB
-    if (tid == 0) carry_s = 0;
-    __syncthreads();
-    for (size_t base = 0; base < P; base += SORT_THREADS) {
-        const size_t i = base + tid;
-        const bool ok = i < P;
+    unsigned run = before;
+    for (size_t i = beg; i < end; i += 32) {
+        const bool ok = i + lane < end;
         unsigned long long key = 0;
-        int pay = 0;
         bool head = false;
         if (ok) {
-            key = kA[i];
-            pay = pA[i];
-            head = (i == 0) || (kA[i - 1] != key);
+            key = k[i + lane];
+            head = (i + lane == 0) || (k[i + lane - 1] != key);
         }
         const unsigned bal = __ballot_sync(0xffffffffu, head);
-        const unsigned excl_w = __popc(bal & ((1u << lane) - 1u));
-        if (lane == 0) wtot[warp] = __popc(bal);
-        __syncthreads();
-        unsigned pre = 0, tot = 0;
-        for (int w = 0; w < SORT_WARPS; ++w) {
-            const unsigned c = wtot[w];
-            if (w < warp) pre += c;
-            tot += c;
-        }
-        const unsigned carry = carry_s;
         if (ok) {
-            const unsigned vid = carry + pre + excl_w + (head ? 1u : 0u) - 1u;
+            const unsigned vid = run + __popc(bal & ((2u << lane) - 1u)) - 1u;  // inclusive count of heads - 1
             if (head) {
                 ukeys[vid] = key;
-                vstart[vid] = (int)i;
+                vstart[vid] = (int)(i + lane);
             }
-            idx[pay] = (int)vid;
-            if (pA != sp) sp[i] = pay;
+            idx[sp[i + lane]] = (int)vid;
         }
-        __syncthreads();
-        if (tid == 0) carry_s = carry + tot;
-        __syncthreads();
+        run += __popc(bal);
     }
-    if (tid == 0) {
-        const unsigned V = carry_s;
-        vstart[V] = (int)P;
-        at<int>(ws, L.hdr)[b] = (int)V;
+    if (warp == 0 && lane == 0) {
+        vstart[total] = (int)P;
+        at<int>(ws, L.hdr)[b] = (int)total;
     }
 }
 
@@ -548,7 +588,16 @@ extern "C" int irb_bg_build(const float* guide, float guide_scale, int B, int H,
     // sort all 64 bits so that aliasing hashes are still ordered exactly like np.unique orders them
     const double maxc = fmax(fmax((double)W / sigma_spatial, (double)H / sigma_spatial), fmax(256.0 / sigma_luma, 384.0 / sigma_chroma));
     const int npass = maxc < 254.0 ? 5 : 7;  // odd: the sorted result must land in keysB / payB
-    bg_sort_unique_kernel<<<B, SORT_THREADS, 0, st>>>(ws, L, npass);
+    {
+        const dim3 sgrid(SORT_WPI / SORT_CTA_WARPS, (unsigned)B);
+        for (int pass = 0; pass < npass; ++pass) {
+            bg_sort_hist_kernel<<<sgrid, SORT_CTA_WARPS * 32, 0, st>>>(ws, L, pass);
+            bg_sort_scan_kernel<<<B, 1024, 0, st>>>(ws, L);
+            bg_sort_scatter_kernel<<<sgrid, SORT_CTA_WARPS * 32, 0, st>>>(ws, L, pass);
+        }
+        bg_unique_count_kernel<<<sgrid, SORT_CTA_WARPS * 32, 0, st>>>(ws, L);
+        bg_unique_rank_kernel<<<sgrid, SORT_CTA_WARPS * 32, 0, st>>>(ws, L);
+    }
     const dim3 grid((unsigned)((L.P + 255) / 256), (unsigned)B);
     bg_nbr_kernel<<<grid, 256, 0, st>>>(ws, L);
     for (int i = 0; i < 10; ++i) bg_bisto_iter_kernel<<<grid, 256, 0, st>>>(ws, L, i & 1);

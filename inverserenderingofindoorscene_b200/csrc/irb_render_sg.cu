@@ -219,13 +219,18 @@ static int launch_tma(KernelT kernel, const RenderSgArgs& a, const EnvTab& tab, 
     return check_launch(what);
 }
 
-// IRB_RENDER_VARIANT = group (default: lobe-split persistent kernels + irregular-pixel follow-up), tma1, plain
-static int render_variant() {
+// Kernel variant.  Measured on B200 (profiles/r01): forward is fastest lobe-split (16 warps/SM keep the MUFU pipe
+// busier); backward with K <= 12 is fastest with all lobes in one thread (fewer instructions, no shuffles), while
+// K > 12 needs the lobe split (otherwise three sweeps).  IRB_RENDER_VARIANT = group | tma1 | plain overrides (A/B).
+//   returns 0 = group (+ irregular-pixel follow-up), 1 = tma1 (single thread per pixel, staged), 2 = plain
+static int render_variant(bool bwd, int K) {
     const char* v = getenv("IRB_RENDER_VARIANT");
-    if (!v) return 0;
-    if (v[0] == 't') return 1;
-    if (v[0] == 'p') return 2;
-    return 0;
+    if (v) {
+        if (v[0] == 'g') return 0;
+        if (v[0] == 't') return 1;
+        if (v[0] == 'p') return 2;
+    }
+    return (bwd && K <= 12) ? 1 : 0;
 }
 
 static int check_common(const RenderSgArgs& a, int envH, int envW, EnvTab& tab) {
@@ -262,7 +267,7 @@ extern "C" int irb_render_sg_fwd(const float* albedo, const float* normal, const
     if (int rc = check_common(a, envH, envW, tab)) return rc;
     IRB_REQUIRE(out_diff && out_spec, "render_sg_fwd: null output pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    const int variant = tma_ok(a, false) ? render_variant() : 2;
+    const int variant = tma_ok(a, false) ? render_variant(false, K) : 2;
     if (variant == 1) {
         if (K <= 12) return launch_tma(render_sg_tma_kernel<0, 12, 12, false, false>, a, tab, false, st, "render_sg_fwd(tma)");
         return launch_tma(render_sg_tma_kernel<0, 24, 24, false, false>, a, tab, false, st, "render_sg_fwd(tma)");
@@ -299,7 +304,7 @@ extern "C" int irb_render_sg_bwd(const float* albedo, const float* normal, const
     const bool lobe = g_axis || g_lamb || g_weight || g_albedo;
     if (!pix && !lobe) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    const int variant = tma_ok(a, true) ? render_variant() : 2;
+    const int variant = tma_ok(a, true) ? render_variant(true, K) : 2;
     if (variant == 1) {
         const char* w = "render_sg_bwd(tma)";
         if (K <= 12) {
