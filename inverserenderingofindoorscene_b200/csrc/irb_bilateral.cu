@@ -9,7 +9,8 @@
 //   vstart[V+1] segment starts, ukeys[V] sorted unique hashes, nbr[10][P] (+-1 neighbour per dim, -1 = none)
 //   n[P], m[P]  bistochastisation vectors (fp64);  solver vectors x,r,p,q,b (fp64, per channel)
 // Arithmetic is fp64 like the reference (NumPy/SciPy doubles); the vertex indexing is integer-exact.
-// Per-iteration structure of PCG: 2 kernels (p-update + mat-vec + <p,q>;  x/r update + <r,z>, <r,r>),
+// Per-iteration structure of PCG: 3 kernels (p-update writing n*p channel-interleaved; mat-vec + <p,q>;
+// x/r update + <r,z>, <r,r>),
 // all images and channels batched in each launch, scalars accumulated per (image, channel, iteration).
 #include <stdint.h>
 
@@ -25,7 +26,7 @@ struct BgLayout {
     int B, H, W, ch;
     size_t P;
     size_t hdr, idx, vstart, ukeys, nbr, n0, n1, m, m0, keysA, keysB, payA, payB, hist;
-    size_t wsplat, minv, bvec, r, p0, p1, q, sol, scal, total;
+    size_t wsplat, minv, bvec, r, p0, p1, q, sol, np, scal, total;
 };
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -60,6 +61,7 @@ static BgLayout make_layout(int B, int H, int W, int ch) {
     L.p1 = take(vc);
     L.q = take(vc);
     L.sol = take(vc);  // adjoint solution (backward)
+    L.np = take(8 * 4 * P * Bz);  // n_v * p_v, interleaved [vertex][4 channels]: one 32-byte sector per neighbour gather
     L.scal = take(8 * Bz * BG_MAX_CH * (BG_MAX_ITERS + 2) * 4);
     L.total = o;
     return L;
@@ -454,30 +456,71 @@ __device__ __forceinline__ bool bg_done(void* ws, const BgLayout& L, int b, int 
     return bb == 0.0 || s[2] < tol * tol * bb || s[0] == 0.0;
 }
 
-// iteration `it`, first half:  p = z + (rho/rho_prev) p ;  q = A p ; pq = <p,q>
-__global__ void bg_pq_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
+// iteration `it`, step 1:  p = z + (rho/rho_prev) p   (z = M r);  also np[v][c] = n_v p_v[c], interleaved over
+// channels so that the mat-vec's neighbour gathers fetch all channels of a vertex in ONE 32-byte sector
+__global__ void bg_p_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    const size_t P = L.P;
+    if (t >= (size_t)at<int>(ws, L.hdr)[b]) return;
+    const double nv = at<double>(ws, L.n0)[(size_t)b * P + t];
+    const double mi = at<double>(ws, L.minv)[(size_t)b * P + t];
+    double out[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int c = 0; c < L.ch; ++c) {
+        if (bg_done(ws, L, b, c, it, a.tol)) continue;
+        const size_t o = ((size_t)b * L.ch + c) * P + t;
+        const double z = mi * at<double>(ws, L.r)[o];
+        double pv = z;
+        if (it > 0) {
+            const double beta = scal_ptr(ws, L, b, c, it)[0] / scal_ptr(ws, L, b, c, it - 1)[0];
+            pv = fma(beta, at<double>(ws, (it & 1) ? L.p1 : L.p0)[o], z);
+        }
+        at<double>(ws, (it & 1) ? L.p0 : L.p1)[o] = pv;
+        out[c] = nv * pv;
+    }
+    double4* np = at<double4>(ws, L.np) + (size_t)b * P + t;
+    *np = make_double4(out[0], out[1], out[2], out[3]);
+}
+
+// iteration `it`, step 2:  q = A p = lam (m p - n blur(n p)) + wsplat p ;  pq = <p,q>
+__global__ void bg_q_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     const size_t P = L.P;
     const int V = at<int>(ws, L.hdr)[b];
     const bool ok = t < (size_t)V;
-    const double* n = at<double>(ws, L.n0) + (size_t)b * P;
-    const double* minv = at<double>(ws, L.minv) + (size_t)b * P;
-    const int* nbr = at<int>(ws, L.nbr) + (size_t)b * 2 * BG_DIM * P;
+    double bl[4] = {0.0, 0.0, 0.0, 0.0};
+    double nv = 0.0, mv = 0.0, wsp = 0.0;
+    if (ok) {
+        const double4* np = at<double4>(ws, L.np) + (size_t)b * P;
+        const int* nbr = at<int>(ws, L.nbr) + (size_t)b * 2 * BG_DIM * P;
+        const double4 own = np[t];
+        bl[0] = 2.0 * BG_DIM * own.x; bl[1] = 2.0 * BG_DIM * own.y; bl[2] = 2.0 * BG_DIM * own.z; bl[3] = 2.0 * BG_DIM * own.w;
+#pragma unroll
+        for (int d = 0; d < BG_DIM; ++d) {   // same summation order as bg_blur: per dimension (lo + hi), then accumulate
+            const int lo = nbr[(size_t)(2 * d) * P + t], hi = nbr[(size_t)(2 * d + 1) * P + t];
+            double4 tt = make_double4(0.0, 0.0, 0.0, 0.0);
+            bool any = false;
+            if (lo >= 0) { tt = np[lo]; any = true; }
+            if (hi >= 0) {
+                const double4 u = np[hi];
+                if (any) { tt.x += u.x; tt.y += u.y; tt.z += u.z; tt.w += u.w; } else { tt = u; }
+                any = true;
+            }
+            if (any) { bl[0] += tt.x; bl[1] += tt.y; bl[2] += tt.z; bl[3] += tt.w; }
+        }
+        nv = at<double>(ws, L.n0)[(size_t)b * P + t];
+        mv = at<double>(ws, L.m)[(size_t)b * P + t];
+        wsp = at<double>(ws, L.wsplat)[(size_t)b * P + t];
+    }
     for (int c = 0; c < L.ch; ++c) {
         if (bg_done(ws, L, b, c, it, a.tol)) continue;  // uniform per (image, channel)
         double pq = 0.0;
         if (ok) {
-            const double beta = it > 0 ? scal_ptr(ws, L, b, c, it)[0] / scal_ptr(ws, L, b, c, it - 1)[0] : 0.0;
-            const double* r = at<double>(ws, L.r) + ((size_t)b * L.ch + c) * P;
-            const double* pold = at<double>(ws, (it & 1) ? L.p1 : L.p0) + ((size_t)b * L.ch + c) * P;
-            double* pnew = at<double>(ws, (it & 1) ? L.p0 : L.p1) + ((size_t)b * L.ch + c) * P;
-            auto pfun = [&](size_t j) { return it > 0 ? fma(beta, pold[j], minv[j] * r[j]) : minv[j] * r[j]; };
-            const double q = bg_matvec(pfun, n, nbr, P, t, at<double>(ws, L.m)[(size_t)b * P + t],
-                                       at<double>(ws, L.wsplat)[(size_t)b * P + t], a.lam);
-            const double pv = pfun(t);
-            pnew[t] = pv;
-            at<double>(ws, L.q)[((size_t)b * L.ch + c) * P + t] = q;
+            const size_t o = ((size_t)b * L.ch + c) * P + t;
+            const double pv = at<double>(ws, (it & 1) ? L.p0 : L.p1)[o];
+            const double q = a.lam * (mv * pv - nv * bl[c]) + wsp * pv;
+            at<double>(ws, L.q)[o] = q;
             pq = pv * q;
         }
         block_atomic_add(pq, scal_ptr(ws, L, b, c, it) + 1);
@@ -546,7 +589,8 @@ static int run_pcg(void* ws, const BgLayout& L, SolveArgs a, int maxiter, cudaSt
     bg_setup_kernel<<<grid, 256, 0, st>>>(ws, L, a);
     bg_r0_kernel<<<grid, 256, 0, st>>>(ws, L, a);
     for (int it = 0; it < maxiter; ++it) {
-        bg_pq_kernel<<<grid, 256, 0, st>>>(ws, L, a, it);
+        bg_p_kernel<<<grid, 256, 0, st>>>(ws, L, a, it);
+        bg_q_kernel<<<grid, 256, 0, st>>>(ws, L, a, it);
         bg_xr_kernel<<<grid, 256, 0, st>>>(ws, L, a, it);
     }
     return check_launch("bilateral pcg");
