@@ -36,8 +36,8 @@ ENV_H, ENV_W = 8, 16
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-baseline-rows', type=int, default=0, help='rows of the 240x320 frame for the CPU sample (0=auto)')
@@ -195,7 +195,7 @@ class Clocks(threading.Thread):
                     self.samples.append(f)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.02)
 
     def summary(self):
         if not self.samples:
@@ -329,11 +329,14 @@ def run_ours(args):
         ach = bwd_bytes / (bwd_ms * 1e-3) / 1e9
         clk = clocks.summary()
         sm_mhz = clk.get('sm_mhz') or 1965
-        # instruction model: per (direction, lobe) fwd 6 FMA-pipe ops + 1 MUFU, bwd 15 + 1;
-        # per direction BRDF fwd ~60 / bwd ~190 FMA-pipe ops
-        flop_fwd = 128 * (K * 6 + 60) * 2.0 * npx
-        flop_bwd = 128 * (K * 15 + 190) * 2.0 * npx
+        # instruction model read off the SASS of the two kernels (profiles/r01): FMA-pipe instructions per pixel
+        # and direction -- forward 12 lobes x 5 + ~50 BRDF = 110, backward 12 x 13 + ~95 = 250; 2 FLOP each
+        flop_fwd = 128 * 110 * 2.0 * npx
+        flop_bwd = 128 * 250 * 2.0 * npx
         fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6
+        # DRAM traffic of the backward kernel from the committed ncu --set full capture of this config
+        # (profiles/r01/ncu_prof_tma1_bwd_summary.txt: dram read 481.4 MB + write 397.0 MB per launch)
+        traffic_bwd = 481.377792e6 + 397.044224e6 if (B, H, W, K) == (16, 240, 320, 12) else None
         line = {
             'metric': 'Mpixels/s render-layer fwd+bwd (240x320, 12 SG)', 'value': value, 'unit': 'Mpix/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_step,
@@ -343,12 +346,14 @@ def run_ours(args):
                        'global_batch': B * world, 'grid': [H, W], 'sg_lobes': K, 'parallelism': 'batch-shard x%d' % world,
                        'l2': 'inputs per step (447 MB/GPU) exceed the 126 MB L2; no explicit flush'},
             'kernel_ms': {'render_sg_fwd': fwd_ms, 'render_sg_bwd': bwd_ms},
-            'roofline': {'bound': 'hbm', 'kernel': 'render_sg_bwd_kernel', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
-                         'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
+            'roofline': {'bound': 'hbm', 'kernel': 'render_sg_tma_kernel<1,12,12,1,1> (fused backward)', 'achieved': ach,
+                         'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': traffic_bwd,
+                         'traffic_source': 'profiles/r01 ncu --set full capture (dram__bytes_read+write per launch)',
+                         'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': bwd_bytes,
                          'fwd': {'achieved': fwd_bytes / (fwd_ms * 1e-3) / 1e9, 'algorithmic_bytes_per_launch': fwd_bytes},
-                         'fp32': {'note': 'kernel is FP32-FMA/MUFU bound (~100 FLOP/B); instruction-model FLOP/s '
-                                          'vs 148 SM x 128 lanes x 2 x sm clock',
+                         'fp32': {'note': 'kernel is FP32-FMA/MUFU bound, not HBM bound (DESIGN.md 4.1): FMA-pipe '
+                                          'instruction model x 2 FLOP vs 148 SM x 128 lanes x 2 x sm clock',
                                   'bwd_tflops': flop_bwd / (bwd_ms * 1e-3) / 1e12,
                                   'fwd_tflops': flop_fwd / (fwd_ms * 1e-3) / 1e12,
                                   'peak_tflops': fp32_peak / 1e12,
@@ -356,7 +361,7 @@ def run_ours(args):
                                   'fwd_frac': flop_fwd / (fwd_ms * 1e-3) / fp32_peak}},
             'e2e': {'value': world * npx / (e2e_ms * 1e-3) / 1e6, 'unit': 'Mpix/s', 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': n_e2e},
-            'gpu_launches': 2 * args.steps,
+            'gpu_launches': 3 * args.steps,   # fwd: lobe-split kernel + irregular-pixel follow-up; bwd: 1 kernel
             'clocks': clk,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -102,8 +102,11 @@ __device__ __forceinline__ void group_tile_fwd(const RenderSgArgs& a, const Rend
     Lobes<float, kLPT> L;
     load_lobes(L, sv, vi.b, vi.pix, vi.plane, h * kLPT);
     float U[kLPT], V[kLPT];
+    LobesPk<kLPT> Lp;
+    pack_lobes<kLPT>(Lp, L);
+    pk2 U2[kLPT / 2], V2[kLPT / 2];
 #pragma unroll
-    for (int k = 0; k < kLPT; ++k) U[k] = V[k] = 0.f;
+    for (int i = 0; i < kLPT / 2; ++i) U2[i] = V2[i] = pk(0.f, 0.f);
     for (int m = 0; m < tab.D; m += TPP) {
         const int dm = m + h;
         DirL<float> dr;
@@ -115,14 +118,20 @@ __device__ __forceinline__ void group_tile_fwd(const RenderSgArgs& a, const Rend
             const float spec = __shfl_sync(0xffffffffu, dr.spec, lane_base + j);
             const float w = tab.w[d] * wz;
             const float ws = w * spec;
-            float arg[kLPT], e[kLPT];
-            lobe_exps<float, kLPT>(L, wx, wy, wz, arg, e);
+            pk2 arg[kLPT / 2], e[kLPT / 2];
+            lobe_exps_pk<kLPT>(Lp, pk(wx, wx), pk(wy, wy), pk(wz, wz), arg, e);
+            const pk2 w2 = pk(w, w), ws2 = pk(ws, ws);
 #pragma unroll
-            for (int k = 0; k < kLPT; ++k) {
-                U[k] += w * e[k];
-                V[k] += ws * e[k];
+            for (int i = 0; i < kLPT / 2; ++i) {
+                U2[i] = fma2(w2, e[i], U2[i]);
+                V2[i] = fma2(ws2, e[i], V2[i]);
             }
         }
+    }
+#pragma unroll
+    for (int i = 0; i < kLPT / 2; ++i) {
+        upk(U2[i], U[2 * i], U[2 * i + 1]);
+        upk(V2[i], V[2 * i], V[2 * i + 1]);
     }
     float Dc[3] = {0.f, 0.f, 0.f}, Sc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -180,8 +189,12 @@ __device__ __forceinline__ void group_tile_bwd(const RenderSgArgs& a, const Rend
         }
         load_lobes(L, sv, vi.b, vi.pix, vi.plane, h * kLPT);
         load_PQ<float, kLPT>(P, Q, sv, vi.b, vi.pix, vi.plane, h * kLPT, gDa, gS);
-#pragma unroll
-        for (int k = 0; k < kLPT; ++k) lg.U[k] = lg.V[k] = lg.S[k] = lg.mx[k] = lg.my[k] = lg.mz[k] = 0.f;
+        LobesPk<kLPT> Lp;
+        pack_lobes<kLPT>(Lp, L);
+        pk2 P2[kLPT / 2], Q2[kLPT / 2];
+        pack_pq<kLPT>(P2, Q2, P, Q);
+        LobeGradsPk<kLPT> g2;
+        gradspk_zero<kLPT>(g2);
         for (int m = 0; m < tab.D; m += TPP) {
             const int dm = m + h;
             const float wxm = ts.lx[dm], wym = ts.ly[dm], wzm = ts.lz[dm];
@@ -194,14 +207,14 @@ __device__ __forceinline__ void group_tile_bwd(const RenderSgArgs& a, const Rend
                 const float wx = tab.lx[d], wy = tab.ly[d], wz = tab.lz[d];
                 const float spec = __shfl_sync(0xffffffffu, dr.spec, lane_base + j);
                 const float w = tab.w[d] * wz;
-                float sP_unused;
-                part[j] = lobes_bwd_dir<float, kLPT, PIX, LOBE>(lg, L, P, Q, wx, wy, wz, w, spec, sP_unused);
+                part[j] = lobes_bwd_dir_pk<kLPT, PIX, LOBE>(g2, Lp, P2, Q2, wx, wy, wz, w, spec);
             }
             if (PIX) {
                 const float sQm = grp_reduce_scatter<TPP>(part, h);
                 dir_bwd_local(gl, px, pl, dr, wxm, wym, wzm, ts.w[dm] * wzm * sQm);
             }
         }
+        gradspk_unpack<kLPT>(lg, g2);
     }
     // epilogue: outputs are predicated per thread by nulling the pointers of inactive threads
     RenderSgArgs ao = a;
