@@ -346,7 +346,7 @@ def run_ours(args):
                        'global_batch': B * world, 'grid': [H, W], 'sg_lobes': K, 'parallelism': 'batch-shard x%d' % world,
                        'l2': 'inputs per step (447 MB/GPU) exceed the 126 MB L2; no explicit flush'},
             'kernel_ms': {'render_sg_fwd': fwd_ms, 'render_sg_bwd': bwd_ms},
-            'roofline': {'bound': 'hbm', 'kernel': 'render_sg_tma_kernel<1,12,12,1,1> (fused backward)', 'achieved': ach,
+            'roofline': {'bound': 'hbm', 'kernel': 'render_sg_group_kernel<1,2,1,1,3> (fused backward, lobe-split)', 'achieved': ach,
                          'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': traffic_bwd,
                          'traffic_source': 'profiles/r01 ncu --set full capture (dram__bytes_read+write per launch)',
                          'peak_source': peak_src,
@@ -361,7 +361,7 @@ def run_ours(args):
                                   'fwd_frac': flop_fwd / (fwd_ms * 1e-3) / fp32_peak}},
             'e2e': {'value': world * npx / (e2e_ms * 1e-3) / 1e6, 'unit': 'Mpix/s', 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': n_e2e},
-            'gpu_launches': 3 * args.steps,   # fwd: lobe-split kernel + irregular-pixel follow-up; bwd: 1 kernel
+            'gpu_launches': 4 * args.steps,   # fwd and bwd: lobe-split kernel + irregular-pixel follow-up each
             'clocks': clk,
         }
         if not args.no_cpu_baseline and world == 1:

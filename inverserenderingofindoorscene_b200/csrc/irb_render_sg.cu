@@ -219,18 +219,19 @@ static int launch_tma(KernelT kernel, const RenderSgArgs& a, const EnvTab& tab, 
     return check_launch(what);
 }
 
-// Kernel variant.  Measured on B200 (profiles/r01): forward is fastest lobe-split (16 warps/SM keep the MUFU pipe
-// busier); backward with K <= 12 is fastest with all lobes in one thread (fewer instructions, no shuffles), while
-// K > 12 needs the lobe split (otherwise three sweeps).  IRB_RENDER_VARIANT = group | tma1 | plain overrides (A/B).
-//   returns 0 = group (+ irregular-pixel follow-up), 1 = tma1 (single thread per pixel, staged), 2 = plain
+// Kernel variant.  Measured on B200 (profiles/r01, config 2): lobe-split "group" kernels 1.03 ms fwd / 2.26 ms bwd,
+// single-thread-per-pixel staged "tma1" 1.10 / 2.38 ms, plain (no staging) 1.23 / 3.41 ms -> group is the default.
+// IRB_RENDER_VARIANT = group | tma1 | plain overrides it (A/B runs and tests).
+//   returns 0 = group (+ irregular-pixel follow-up), 1 = tma1, 2 = plain
 static int render_variant(bool bwd, int K) {
+    (void)bwd;
+    (void)K;
     const char* v = getenv("IRB_RENDER_VARIANT");
     if (v) {
-        if (v[0] == 'g') return 0;
         if (v[0] == 't') return 1;
         if (v[0] == 'p') return 2;
     }
-    return (bwd && K <= 12) ? 1 : 0;
+    return 0;
 }
 
 static int check_common(const RenderSgArgs& a, int envH, int envW, EnvTab& tab) {
