@@ -137,6 +137,32 @@ __device__ __forceinline__ float lobes_bwd_dir_pk(LobeGradsPk<KC>& g, const Lobe
     upk(sQ2, a, b);
     return a + b;
 }
+// accumulation phase only (arguments / exponentials precomputed by lobe_exps_pk)
+template <int KC, bool PIX, bool LOBE>
+__device__ __forceinline__ float lobes_bwd_acc_pk(LobeGradsPk<KC>& g, const pk2 (&P2)[KC / 2], const pk2 (&Q2)[KC / 2],
+                                                  const pk2 (&arg)[KC / 2], const pk2 (&e)[KC / 2], float wx, float wy, float wz,
+                                                  float w, float spec) {
+    const pk2 wx2 = pk(wx, wx), wy2 = pk(wy, wy), wz2 = pk(wz, wz);
+    const pk2 w2 = pk(w, w), sp2 = pk(spec, spec);
+    pk2 sQ2 = pk(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < KC / 2; ++i) {
+        if (PIX) sQ2 = fma2(Q2[i], e[i], sQ2);
+        if (LOBE) {
+            const pk2 ew = mul2(e[i], w2);
+            g.U[i] = add2(g.U[i], ew);
+            g.V[i] = fma2(ew, sp2, g.V[i]);
+            const pk2 t = mul2(ew, fma2(sp2, Q2[i], P2[i]));
+            g.S[i] = fma2(t, arg[i], g.S[i]);
+            g.mx[i] = fma2(t, wx2, g.mx[i]);
+            g.my[i] = fma2(t, wy2, g.my[i]);
+            g.mz[i] = fma2(t, wz2, g.mz[i]);
+        }
+    }
+    float a, b;
+    upk(sQ2, a, b);
+    return a + b;
+}
 template <int KC> __device__ __forceinline__ void gradspk_zero(LobeGradsPk<KC>& g) {
 #pragma unroll
     for (int i = 0; i < KC / 2; ++i) g.U[i] = g.V[i] = g.S[i] = g.mx[i] = g.my[i] = g.mz[i] = pk(0.f, 0.f);

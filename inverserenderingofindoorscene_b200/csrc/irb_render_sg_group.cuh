@@ -111,20 +111,26 @@ __device__ __forceinline__ void group_tile_fwd(const RenderSgArgs& a, const Rend
         const int dm = m + h;
         DirL<float> dr;
         dir_fwd_local(dr, px, pl, ts.lx[dm], ts.ly[dm], ts.lz[dm]);
+        pk2 e[TPP][kLPT / 2];
+        pk2 w2[TPP], ws2[TPP];
 #pragma unroll
-        for (int j = 0; j < TPP; ++j) {
+        for (int j = 0; j < TPP; ++j) {   // all arguments and exponentials of the TPP directions first: TPP*3 independent chains
             const int d = m + j;
             const float wx = tab.lx[d], wy = tab.ly[d], wz = tab.lz[d];
             const float spec = __shfl_sync(0xffffffffu, dr.spec, lane_base + j);
             const float w = tab.w[d] * wz;
             const float ws = w * spec;
-            pk2 arg[kLPT / 2], e[kLPT / 2];
-            lobe_exps_pk<kLPT>(Lp, pk(wx, wx), pk(wy, wy), pk(wz, wz), arg, e);
-            const pk2 w2 = pk(w, w), ws2 = pk(ws, ws);
+            pk2 arg[kLPT / 2];
+            lobe_exps_pk<kLPT>(Lp, pk(wx, wx), pk(wy, wy), pk(wz, wz), arg, e[j]);
+            w2[j] = pk(w, w);
+            ws2[j] = pk(ws, ws);
+        }
+#pragma unroll
+        for (int j = 0; j < TPP; ++j) {
 #pragma unroll
             for (int i = 0; i < kLPT / 2; ++i) {
-                U2[i] = fma2(w2, e[i], U2[i]);
-                V2[i] = fma2(ws2, e[i], V2[i]);
+                U2[i] = fma2(w2[j], e[j][i], U2[i]);
+                V2[i] = fma2(ws2[j], e[j][i], V2[i]);
             }
         }
     }
@@ -201,13 +207,20 @@ __device__ __forceinline__ void group_tile_bwd(const RenderSgArgs& a, const Rend
             DirL<float> dr;
             dir_fwd_local(dr, px, pl, wxm, wym, wzm);
             float part[TPP];
+            pk2 arg[TPP][kLPT / 2], e[TPP][kLPT / 2];
+            float spec[TPP];
 #pragma unroll
-            for (int j = 0; j < TPP; ++j) {
+            for (int j = 0; j < TPP; ++j) {   // phase 1: arguments + exponentials of all TPP directions (TPP*3 independent chains)
                 const int d = m + j;
                 const float wx = tab.lx[d], wy = tab.ly[d], wz = tab.lz[d];
-                const float spec = __shfl_sync(0xffffffffu, dr.spec, lane_base + j);
-                const float w = tab.w[d] * wz;
-                part[j] = lobes_bwd_dir_pk<kLPT, PIX, LOBE>(g2, Lp, P2, Q2, wx, wy, wz, w, spec);
+                spec[j] = __shfl_sync(0xffffffffu, dr.spec, lane_base + j);
+                lobe_exps_pk<kLPT>(Lp, pk(wx, wx), pk(wy, wy), pk(wz, wz), arg[j], e[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < TPP; ++j) {   // phase 2: accumulations
+                const int d = m + j;
+                const float wx = tab.lx[d], wy = tab.ly[d], wz = tab.lz[d];
+                part[j] = lobes_bwd_acc_pk<kLPT, PIX, LOBE>(g2, P2, Q2, arg[j], e[j], wx, wy, wz, tab.w[d] * wz, spec[j]);
             }
             if (PIX) {
                 const float sQm = grp_reduce_scatter<TPP>(part, h);
