@@ -176,36 +176,78 @@ def run_reference(args):
 # -------------------------------------------------------------------------------------------
 
 class Clocks(threading.Thread):
+    """samples SM clock + throttle reasons DURING the timed region: NVML in-process (sub-millisecond per sample),
+    nvidia-smi as fallback"""
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.samples = []     # (sm_mhz, max_mhz, [reason names])
         self.stop_flag = False
+        self.source = 'nvml'
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # honour CUDA_VISIBLE_DEVICES-style remapping: take the handle by the torch device's PCI bus id
+            import torch as _t
+            prop = _t.cuda.get_device_properties(index)
+            bus = getattr(prop, 'pci_bus_id', None)
+            self.h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hh = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(hh).bus == bus:
+                        self.h = hh
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nv = None
+            self.source = 'nvidia-smi'
+
+    def _sample_nvml(self):
+        nv = self.nv
+        sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        names = []
+        for bit, name in ((0x8, 'hw_slowdown'), (0x40, 'hw_thermal_slowdown'), (0x20, 'sw_thermal_slowdown'),
+                          (0x4, 'sw_power_cap')):
+            if r & bit:
+                names.append(name)
+        self.samples.append((sm, mx, names))
+
+    def _sample_smi(self):
+        out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                              '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+        f = [x.strip() for x in out.strip().split(',')]
+        if len(f) >= 6 and f[0].isdigit():
+            names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+            self.samples.append((int(f[0]), int(f[1]), [n for i, n in enumerate(names) if f[2 + i].lower().startswith('active')]))
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(',')]
-                if len(f) >= 6:
-                    self.samples.append(f)
+                if self.nv is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.005)
 
     def summary(self):
         if not self.samples:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        mx = max(int(s[1]) for s in self.samples if s[1].isdigit())
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith('active') for s in self.samples)]
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': reasons,
-                'samples': len(self.samples)}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = sorted(set(n for s in self.samples for n in s[2]))
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': max(s[1] for s in self.samples), 'reasons': reasons,
+                'samples': len(self.samples), 'source': self.source}
 
 
 # -------------------------------------------------------------------------------------------
