@@ -255,3 +255,50 @@ def test_tma_ring_many_tiles_per_cta(irb, cap, monkeypatch):
     g64 = torch.autograd.grad((d64 * gD.cpu().double()).sum() + (s64 * gS.cpu().double()).sum(), ins64)
     for a, b in zip(tma, [d64, s64] + list(g64)):
         assert relerr(a.cpu().numpy(), b.detach().numpy()) <= 2e-4
+
+
+def test_trainlight_loss_step_vs_oracle(irb):
+    """wrapperBRDFLight.py:170-207 end to end through the drop-in classes: output2env (env-map materialised for
+    reconstErr) -> forwardEnv (fused dispatch via the SG provenance of the env tensor) -> LSregressDiffSpec -> render
+    + reconstruction losses -> backward.  Loss values and the SG-parameter gradients (sum of both gradient paths)
+    against the fp64 oracle."""
+    from oracle import render_oracle as ro
+    B, H, W, R, C, K = 2, 24, 32, 12, 16, 12
+    ins64 = ro.synth_inputs(B, H, W, R, C, K, seed=2024, dtype=torch.float64, hi=0.9)
+    g = torch.Generator().manual_seed(11)
+    im = torch.rand(B, 3, R, C, generator=g, dtype=torch.float64)
+    seg = (torch.rand(B, 1, R, C, generator=g) > 0.2).double()
+    envgt = torch.rand(B, 3, R, C, 8, 16, generator=g, dtype=torch.float64) * 2
+    segenv = seg.unsqueeze(-1).unsqueeze(-1)
+
+    def run(mod_out2env, mod_render, lsreg, lsreg_ds, ins, im, seg, envgt, segenv):
+        alb, nrm, rg, ax, lam, wt = ins
+        env = mod_out2env(ax, lam, wt)
+        pixelNum = max(float(segenv.sum()), 1e-5)
+        m = segenv.expand_as(envgt)
+        envs = lsreg(env.detach() * m, envgt * m, env)
+        dl = torch.log(envs + 1.0) - torch.log(envgt + 1.0)
+        reconst = (dl * dl * m).sum() / pixelNum / 3.0 / 16 / 8
+        pixelNum = max(float(seg.sum()), 1e-5)
+        d, s = mod_render(alb.detach(), nrm, rg, env)
+        dS, sS = lsreg_ds(d.detach(), s.detach(), im, d, s)
+        rend = torch.clamp(dS + sS, 0, 1)
+        rerr = ((rend - im) * (rend - im) * seg.expand_as(im)).sum() / pixelNum / 3.0
+        return rerr, reconst
+
+    ins_o = [t.clone().requires_grad_(True) for t in ins64]
+    r64, c64 = run(lambda a, l, w: ro.output2env(a, l, w)[0], lambda a, n, r, e: ro.render_env(a, n, r, e), ro.ls_regress,
+                   ro.ls_regress_diff_spec, ins_o, im, seg, envgt, segenv)
+    (r64 + 10 * c64).backward()
+    dev = torch.device('cuda')
+    ins_g = [t.detach().float().to(dev).requires_grad_(True) for t in ins64]
+    rl = irb.renderingLayer(imWidth=C, imHeight=R, isCuda=True)
+    o2e = irb.output2env(K, isCuda=True)
+    rg_, cg_ = run(lambda a, l, w: o2e.output2env(a, l, w)[0], rl.forwardEnv, irb.LSregress, irb.LSregressDiffSpec, ins_g,
+                   im.float().to(dev), seg.float().to(dev), envgt.float().to(dev), segenv.float().to(dev))
+    (rg_ + 10 * cg_).backward()
+    assert abs(float(rg_) - float(r64)) <= 1e-4 * abs(float(r64))
+    assert abs(float(cg_) - float(c64)) <= 1e-4 * abs(float(c64))
+    for i, name in ((1, 'normal'), (2, 'rough'), (3, 'axis'), (4, 'lamb'), (5, 'weight')):
+        assert relerr(ins_g[i].grad.cpu().numpy(), ins_o[i].grad.numpy()) <= 3e-4, name
+    assert ins_g[0].grad is None     # albedo is detached in the trainLight step
