@@ -302,3 +302,77 @@ def test_trainlight_loss_step_vs_oracle(irb):
     for i, name in ((1, 'normal'), (2, 'rough'), (3, 'axis'), (4, 'lamb'), (5, 'weight')):
         assert relerr(ins_g[i].grad.cpu().numpy(), ins_o[i].grad.numpy()) <= 3e-4, name
     assert ins_g[0].grad is None     # albedo is detached in the trainLight step
+
+
+@pytest.mark.parametrize('K', [1, 5, 6, 7, 12, 13, 24])
+def test_lobe_counts_group_kernels(irb, K):
+    """every lobe-split configuration (TPP = 1, 2, 4; padded last group) against the fp64 oracle, with a few
+    irregular pixels mixed in (handled by the follow-up launch)"""
+    from oracle import render_oracle as ro
+    B, R, C = 2, 8, 12
+    ins64 = ro.synth_inputs(B, R, C, R, C, K, seed=500 + K, dtype=torch.float64, hi=0.95)
+    ins64[1][0, :, 0, 0] = torch.tensor([0.0, 0.0, 0.0])
+    ins64[1][1, :, 3, 5] = torch.tensor([0.2, 0.1, 1.3])
+    ins64 = [t.float().double().requires_grad_(True) for t in ins64]
+    g = torch.Generator().manual_seed(K)
+    gD = torch.rand(B, 3, R, C, generator=g)
+    gS = torch.rand(B, 3, R, C, generator=g)
+    d64, s64 = ro.render_sg(*ins64)
+    g64 = torch.autograd.grad((d64 * gD.double()).sum() + (s64 * gS.double()).sum(), ins64)
+    dev = torch.device('cuda')
+    ins = [t.detach().float().to(dev).requires_grad_(True) for t in ins64]
+    rl = irb.renderingLayer(imWidth=C, imHeight=R, isCuda=True)
+    d, s = rl.forwardSG(*ins)
+    gg = torch.autograd.grad([d, s], ins, [gD.to(dev), gS.to(dev)])
+    assert relerr(d.detach().cpu().numpy(), d64.detach().numpy()) <= 1e-4
+    assert relerr(s.detach().cpu().numpy(), s64.detach().numpy()) <= 1e-4
+    for a, b, name in zip(gg, g64, ('albedo', 'normal', 'rough', 'axis', 'lamb', 'weight')):
+        assert relerr(a.cpu().numpy(), b.numpy()) <= 3e-4, name
+
+
+@pytest.mark.parametrize('envH,envW', [(4, 8), (8, 8), (2, 16)])
+def test_other_env_tables(irb, envH, envW):
+    """hemisphere tables other than 8x16 (models.py ctor kwargs envWidth / envHeight), fused and unfused"""
+    from oracle import render_oracle as ro
+    B, R, C, K = 1, 6, 8, 12
+    ins64 = ro.synth_inputs(B, R, C, R, C, K, seed=77, dtype=torch.float64, hi=0.9)
+    for t in ins64:
+        t.requires_grad_(True)
+    d64, s64 = ro.render_sg(*ins64, envHeight=envH, envWidth=envW)
+    g64 = torch.autograd.grad(d64.sum() + 2 * s64.sum(), ins64)
+    dev = torch.device('cuda')
+    rl = irb.renderingLayer(imWidth=C, imHeight=R, envWidth=envW, envHeight=envH, isCuda=True)
+    o2e = irb.output2env(K, envWidth=envW, envHeight=envH, isCuda=True)
+    for fused in (True, False):
+        ins = [t.detach().float().to(dev).requires_grad_(True) for t in ins64]
+        env, _, _, _ = o2e.output2env(ins[3], ins[4], ins[5])
+        assert tuple(env.shape) == (B, 3, R, C, envH, envW)
+        d, s = rl.forwardEnv(ins[0], ins[1], ins[2], env if fused else env * 1.0)
+        gg = torch.autograd.grad(d.sum() + 2 * s.sum(), ins)
+        assert relerr(d.detach().cpu().numpy(), d64.detach().numpy()) <= 1e-4
+        assert relerr(s.detach().cpu().numpy(), s64.detach().numpy()) <= 1e-4
+        for a, b in zip(gg, g64):
+            assert relerr(a.cpu().numpy(), b.numpy()) <= 3e-4
+
+
+def test_noncontiguous_and_needs_grad_subsets(irb):
+    """non-contiguous inputs are made contiguous by the shim; only the requested gradients are produced"""
+    from oracle import render_oracle as ro
+    B, R, C, K = 2, 6, 8, 12
+    ins64 = ro.synth_inputs(B, R, C, R, C, K, seed=31, dtype=torch.float64, hi=0.9)
+    dev = torch.device('cuda')
+    alb, nrm, rg, ax, lam, wt = [t.float().to(dev) for t in ins64]
+    rl = irb.renderingLayer(imWidth=C, imHeight=R, isCuda=True)
+    d0, s0 = rl.forwardSG(alb, nrm, rg, ax, lam, wt)
+    ax_nc = ax.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)   # same values, non-contiguous strides
+    assert not ax_nc.is_contiguous()
+    d1, s1 = rl.forwardSG(alb, nrm, rg, ax_nc, lam, wt)
+    assert torch.equal(d0, d1) and torch.equal(s0, s1)
+    lam_g = lam.clone().requires_grad_(True)
+    d2, s2 = rl.forwardSG(alb, nrm, rg, ax, lam_g, wt)
+    (d2.sum() + s2.sum()).backward()
+    assert lam_g.grad is not None and torch.isfinite(lam_g.grad).all()
+    nrm_g = nrm.clone().requires_grad_(True)
+    d3, s3 = rl.forwardSG(alb, nrm_g, rg, ax, lam, wt)
+    (d3.sum() + s3.sum()).backward()
+    assert nrm_g.grad is not None and torch.isfinite(nrm_g.grad).all()
