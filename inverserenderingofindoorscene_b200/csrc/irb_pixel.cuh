@@ -187,6 +187,114 @@ template <int KC> __device__ __forceinline__ void pack_pq(pk2 (&P2)[KC / 2], pk2
 }
 #endif  // __CUDACC__
 
+#if defined(__CUDACC__)
+// ---- packed (two directions per instruction) local-frame BRDF: dir_fwd_local / dir_bwd_local on f32x2 ----------
+// Same formulas as irb_math.cuh, evaluated for directions (d0, d1) in the two halves of 64-bit register pairs; the
+// special-function ops and the clamps/selects work on the halves.
+struct DirL2 {
+    pk2 Mx, My, Mz, rinv, vdh, p2, F, ndh_raw, ndh, n0, n2, nom_raw, inv_nom, spec;
+    bool ok0, ok1;  // m.m clamp inactive (per half)
+};
+__device__ __forceinline__ pk2 pkb(float a) { return pk(a, a); }
+__device__ __forceinline__ pk2 sel2(bool c0, bool c1, pk2 a, pk2 b) {
+    float a0, a1, b0, b1;
+    upk(a, a0, a1);
+    upk(b, b0, b1);
+    return pk(c0 ? a0 : b0, c1 ? a1 : b1);
+}
+__device__ __forceinline__ void dir_fwd_local2(DirL2& dr, const Pixel<float>& px, const PixelLocal<float>& pl, pk2 wx, pk2 wy, pk2 wz) {
+    const pk2 vx = pkb(pl.vx), vy = pkb(pl.vy), vz = pkb(pl.vz);
+    dr.Mx = add2(vx, wx);
+    dr.My = add2(vy, wy);
+    dr.Mz = add2(vz, wz);
+    const pk2 q = fma2(dr.My, dr.My, mul2(dr.Mx, dr.Mx));
+    const pk2 MM = fma2(dr.Mz, dr.Mz, q);
+    float m0, m1;
+    upk(MM, m0, m1);
+    dr.ok0 = m0 >= 4e-6f;
+    dr.ok1 = m1 >= 4e-6f;
+    dr.rinv = pk(x_rsqrt(fmaxf(m0, 4e-6f)), x_rsqrt(fmaxf(m1, 4e-6f)));
+    dr.vdh = mul2(fma2(vz, dr.Mz, fma2(vy, dr.My, mul2(vx, dr.Mx))), dr.rinv);
+    dr.p2 = ex2x2(mul2(fma2(pkb(-5.55472f), dr.vdh, pkb(-6.98316f)), dr.vdh));
+    dr.F = fma2(pkb(1.0f - px.F0), dr.p2, pkb(px.F0));
+    dr.ndh_raw = mul2(dr.Mz, dr.rinv);
+    float r0, r1;
+    upk(dr.ndh_raw, r0, r1);
+    dr.ndh = pk(__saturatef(r0), __saturatef(r1));
+    const pk2 nn = mul2(dr.ndh, dr.ndh);
+    const pk2 a2n = mul2(pkb(px.alpha2), nn);
+    pk2 n0 = fma2(q, mul2(dr.rinv, dr.rinv), a2n);             // 1 - ndh^2 = (Mx^2+My^2)/|M|^2
+    if (!(dr.ok0 && dr.ok1)) n0 = sel2(dr.ok0, dr.ok1, n0, add2(fma2(nn, pkb(-1.0f), a2n), pkb(1.0f)));
+    float n00, n01;
+    upk(n0, n00, n01);
+    dr.n0 = pk(r0 <= 0.f ? 1.0f : (r0 >= 1.0f ? px.alpha2 : n00), r1 <= 0.f ? 1.0f : (r1 >= 1.0f ? px.alpha2 : n01));
+    dr.n2 = fma2(wz, pkb(1.0f - px.k), pkb(px.k));
+    dr.nom_raw = mul2(mul2(pkb(Consts<float>::FOUR_PI * px.n1), mul2(dr.n0, dr.n0)), dr.n2);
+    float q0, q1;
+    upk(dr.nom_raw, q0, q1);
+    dr.inv_nom = pk(x_rcp(fminf(fmaxf(q0, 1e-6f), Consts<float>::FOUR_PI)), x_rcp(fminf(fmaxf(q1, 1e-6f), Consts<float>::FOUR_PI)));
+    dr.spec = mul2(mul2(pkb(px.alpha2), dr.F), dr.inv_nom);
+}
+
+struct PixelGradL2 {
+    pk2 Gxx, Gxy, Gxz, Gyx, Gyy, Gyz, Gzx, Gzy, Gzz, gnx, gny, gnz, G_n1, g_alpha2, g_k;
+};
+__device__ __forceinline__ void pixel_gradl2_zero(PixelGradL2& g) {
+    const pk2 z = pk(0.f, 0.f);
+    g.Gxx = g.Gxy = g.Gxz = g.Gyx = g.Gyy = g.Gyz = g.Gzx = g.Gzy = g.Gzz = z;
+    g.gnx = g.gny = g.gnz = g.G_n1 = g.g_alpha2 = g.g_k = z;
+}
+__device__ __forceinline__ float hsum2(pk2 v) {
+    float a, b;
+    upk(v, a, b);
+    return a + b;
+}
+__device__ __forceinline__ void pixel_gradl2_fold(PixelGradL<float>& o, const PixelGradL2& g) {
+    o.Gxx = hsum2(g.Gxx); o.Gxy = hsum2(g.Gxy); o.Gxz = hsum2(g.Gxz);
+    o.Gyx = hsum2(g.Gyx); o.Gyy = hsum2(g.Gyy); o.Gyz = hsum2(g.Gyz);
+    o.Gzx = hsum2(g.Gzx); o.Gzy = hsum2(g.Gzy); o.Gzz = hsum2(g.Gzz);
+    o.gnx = hsum2(g.gnx); o.gny = hsum2(g.gny); o.gnz = hsum2(g.gnz);
+    o.G_n1 = hsum2(g.G_n1); o.g_alpha2 = hsum2(g.g_alpha2); o.g_k = hsum2(g.g_k);
+}
+// g_spec (two directions) = Omega_d ndl_d sum_k Q_k e_kd
+__device__ __forceinline__ void dir_bwd_local2(PixelGradL2& g, const Pixel<float>& px, const PixelLocal<float>& pl, const DirL2& dr,
+                                               pk2 wx, pk2 wy, pk2 wz, pk2 g_spec) {
+    const pk2 gsi = mul2(g_spec, dr.inv_nom);
+    const pk2 g_F = mul2(gsi, pkb(px.alpha2));
+    g.g_alpha2 = fma2(gsi, dr.F, g.g_alpha2);
+    float q0, q1;
+    upk(dr.nom_raw, q0, q1);
+    const bool p0 = (q0 >= 1e-6f) && (q0 <= Consts<float>::FOUR_PI), p1 = (q1 >= 1e-6f) && (q1 <= Consts<float>::FOUR_PI);
+    pk2 c4 = mul2(mul2(gsi, dr.spec), pkb(-Consts<float>::FOUR_PI));   // g_nom * 4 pi
+    if (!(p0 && p1)) c4 = sel2(p0, p1, c4, pk(0.f, 0.f));
+    const pk2 x = mul2(c4, mul2(dr.n0, dr.n0));
+    g.G_n1 = fma2(x, dr.n2, g.G_n1);
+    g.g_k = fma2(mul2(x, pkb(px.n1)), fma2(wz, pkb(-1.0f), pkb(1.0f)), g.g_k);
+    const pk2 g_n0 = mul2(mul2(c4, pkb(2.0f * px.n1)), mul2(dr.n0, dr.n2));
+    const pk2 g_ndh = mul2(mul2(g_n0, pkb(2.0f * (px.alpha2 - 1.0f))), dr.ndh);
+    g.g_alpha2 = fma2(g_n0, mul2(dr.ndh, dr.ndh), g.g_alpha2);
+    const pk2 g_vdh = mul2(mul2(mul2(g_F, pkb((1.0f - px.F0) * Consts<float>::LN2)), dr.p2),
+                           fma2(pkb(-2.0f * 5.55472f), dr.vdh, pkb(-6.98316f)));
+    float r0, r1;
+    upk(dr.ndh_raw, r0, r1);
+    const bool h0 = (r0 >= 0.f) && (r0 <= 1.f), h1 = (r1 >= 0.f) && (r1 <= 1.f);
+    pk2 g_ndhr = g_ndh;
+    if (!(h0 && h1)) g_ndhr = sel2(h0, h1, g_ndh, pk(0.f, 0.f));
+    const pk2 ghx = mul2(g_vdh, pkb(pl.vx)), ghy = mul2(g_vdh, pkb(pl.vy)), ghz = fma2(g_vdh, pkb(pl.vz), g_ndhr);
+    const pk2 hx = mul2(dr.Mx, dr.rinv), hy = mul2(dr.My, dr.rinv), hz = mul2(dr.Mz, dr.rinv);
+    g.gnx = fma2(g_ndhr, hx, g.gnx);
+    g.gny = fma2(g_ndhr, hy, g.gny);
+    g.gnz = fma2(g_ndhr, hz, g.gnz);
+    pk2 hg = fma2(g_ndhr, dr.ndh_raw, mul2(g_vdh, dr.vdh));
+    if (!(dr.ok0 && dr.ok1)) hg = sel2(dr.ok0, dr.ok1, hg, pk(0.f, 0.f));
+    const pk2 nhg = mul2(hg, pkb(-1.0f));
+    const pk2 glx = mul2(fma2(hx, nhg, ghx), dr.rinv), gly = mul2(fma2(hy, nhg, ghy), dr.rinv), glz = mul2(fma2(hz, nhg, ghz), dr.rinv);
+    g.Gxx = fma2(wx, glx, g.Gxx); g.Gxy = fma2(wx, gly, g.Gxy); g.Gxz = fma2(wx, glz, g.Gxz);
+    g.Gyx = fma2(wy, glx, g.Gyx); g.Gyy = fma2(wy, gly, g.Gyy); g.Gyz = fma2(wy, glz, g.Gyz);
+    g.Gzx = fma2(wz, glx, g.Gzx); g.Gzy = fma2(wz, gly, g.Gzy); g.Gzz = fma2(wz, glz, g.Gzz);
+}
+#endif  // __CUDACC__
+
 template <typename T, int KC>
 IRB_HD void sweep_fwd(const Pixel<T>& px, const Lobes<T, KC>& L, const EnvTab& tab, T (&U)[KC], T (&V)[KC]) {
 #pragma unroll

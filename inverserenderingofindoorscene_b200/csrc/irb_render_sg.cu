@@ -268,7 +268,8 @@ extern "C" int irb_render_sg_fwd(const float* albedo, const float* normal, const
     if (int rc = check_common(a, envH, envW, tab)) return rc;
     IRB_REQUIRE(out_diff && out_spec, "render_sg_fwd: null output pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    const int variant = tma_ok(a, false) ? render_variant(false, K) : 2;
+    int variant = tma_ok(a, false) ? render_variant(false, K) : 2;
+    if (variant == 0 && tab.D % (2 * (K <= 6 ? 1 : (K <= 12 ? 2 : 4))) != 0) variant = 1;  // group kernels walk 2*TPP directions per iteration
     if (variant == 1) {
         if (K <= 12) return launch_tma(render_sg_tma_kernel<0, 12, 12, false, false>, a, tab, false, st, "render_sg_fwd(tma)");
         return launch_tma(render_sg_tma_kernel<0, 24, 24, false, false>, a, tab, false, st, "render_sg_fwd(tma)");
@@ -305,7 +306,8 @@ extern "C" int irb_render_sg_bwd(const float* albedo, const float* normal, const
     const bool lobe = g_axis || g_lamb || g_weight || g_albedo;
     if (!pix && !lobe) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    const int variant = tma_ok(a, true) ? render_variant(true, K) : 2;
+    int variant = tma_ok(a, true) ? render_variant(true, K) : 2;
+    if (variant == 0 && tab.D % (2 * (K <= 6 ? 1 : (K <= 12 ? 2 : 4))) != 0) variant = 1;
     if (variant == 1) {
         const char* w = "render_sg_bwd(tma)";
         if (K <= 12) {
@@ -320,11 +322,12 @@ extern "C" int irb_render_sg_bwd(const float* albedo, const float* normal, const
     if (variant == 0) {
         int rc;
         const char* w = "render_sg_bwd(group)";
-        const char* mb = getenv("IRB_BWD_MINB");  // A/B knob: 4 = cap the backward at 128 registers (spills) for 16 warps/SM
-        const bool minb4 = mb && mb[0] == '4';
+        const char* mb = getenv("IRB_BWD_MINB");  // A/B knob: resident CTAs the full backward is compiled for (2: 255 regs, 3: 168, 4: 128)
+        const int minb = (mb && mb[0] >= '2' && mb[0] <= '4') ? mb[0] - '0' : 2;
 #define IRB_GROUP_BWD(TPP)                                                                                                   \
-    (pix && lobe ? (minb4 ? launch_tma(render_sg_group_kernel<1, TPP, true, true, 4>, a, tab, true, st, w, kThreads / TPP)    \
-                          : launch_tma(render_sg_group_kernel<1, TPP, true, true, 3>, a, tab, true, st, w, kThreads / TPP))   \
+    (pix && lobe ? (minb == 4   ? launch_tma(render_sg_group_kernel<1, TPP, true, true, 4>, a, tab, true, st, w, kThreads / TPP) \
+                    : minb == 3 ? launch_tma(render_sg_group_kernel<1, TPP, true, true, 3>, a, tab, true, st, w, kThreads / TPP) \
+                                : launch_tma(render_sg_group_kernel<1, TPP, true, true, 2>, a, tab, true, st, w, kThreads / TPP)) \
      : pix      ? launch_tma(render_sg_group_kernel<1, TPP, true, false, 3>, a, tab, true, st, w, kThreads / TPP)            \
                 : launch_tma(render_sg_group_kernel<1, TPP, false, true, 3>, a, tab, true, st, w, kThreads / TPP))
         if (K <= 6) rc = IRB_GROUP_BWD(1);

@@ -107,17 +107,21 @@ __device__ __forceinline__ void group_tile_fwd(const RenderSgArgs& a, const Rend
     pk2 U2[kLPT / 2], V2[kLPT / 2];
 #pragma unroll
     for (int i = 0; i < kLPT / 2; ++i) U2[i] = V2[i] = pk(0.f, 0.f);
-    for (int m = 0; m < tab.D; m += TPP) {
-        const int dm = m + h;
-        DirL<float> dr;
-        dir_fwd_local(dr, px, pl, ts.lx[dm], ts.ly[dm], ts.lz[dm]);
-        pk2 e[TPP][kLPT / 2];
-        pk2 w2[TPP], ws2[TPP];
+    // 2*TPP directions per iteration: this lane evaluates the BRDF chains of directions m+h and m+TPP+h packed in
+    // the two halves of f32x2 registers
+    for (int m = 0; m < tab.D; m += 2 * TPP) {
+        const int d0 = m + h, d1 = m + TPP + h;
+        DirL2 dr;
+        dir_fwd_local2(dr, px, pl, pk(ts.lx[d0], ts.lx[d1]), pk(ts.ly[d0], ts.ly[d1]), pk(ts.lz[d0], ts.lz[d1]));
+        float sp_lo, sp_hi;
+        upk(dr.spec, sp_lo, sp_hi);
+        pk2 e[2 * TPP][kLPT / 2];
+        pk2 w2[2 * TPP], ws2[2 * TPP];
 #pragma unroll
-        for (int j = 0; j < TPP; ++j) {   // all arguments and exponentials of the TPP directions first: TPP*3 independent chains
+        for (int j = 0; j < 2 * TPP; ++j) {
             const int d = m + j;
             const float wx = tab.lx[d], wy = tab.ly[d], wz = tab.lz[d];
-            const float spec = __shfl_sync(0xffffffffu, dr.spec, lane_base + j);
+            const float spec = __shfl_sync(0xffffffffu, j < TPP ? sp_lo : sp_hi, lane_base + (j % TPP));
             const float w = tab.w[d] * wz;
             const float ws = w * spec;
             pk2 arg[kLPT / 2];
@@ -126,7 +130,7 @@ __device__ __forceinline__ void group_tile_fwd(const RenderSgArgs& a, const Rend
             ws2[j] = pk(ws, ws);
         }
 #pragma unroll
-        for (int j = 0; j < TPP; ++j) {
+        for (int j = 0; j < 2 * TPP; ++j) {
 #pragma unroll
             for (int i = 0; i < kLPT / 2; ++i) {
                 U2[i] = fma2(w2[j], e[j][i], U2[i]);
@@ -201,32 +205,49 @@ __device__ __forceinline__ void group_tile_bwd(const RenderSgArgs& a, const Rend
         pack_pq<kLPT>(P2, Q2, P, Q);
         LobeGradsPk<kLPT> g2;
         gradspk_zero<kLPT>(g2);
-        for (int m = 0; m < tab.D; m += TPP) {
-            const int dm = m + h;
-            const float wxm = ts.lx[dm], wym = ts.ly[dm], wzm = ts.lz[dm];
-            DirL<float> dr;
-            dir_fwd_local(dr, px, pl, wxm, wym, wzm);
-            float part[TPP];
-            pk2 arg[TPP][kLPT / 2], e[TPP][kLPT / 2];
-            float spec[TPP];
+        PixelGradL2 gl2;
+        pixel_gradl2_zero(gl2);
+        for (int m = 0; m < tab.D; m += 2 * TPP) {
+            const int d0 = m + h, d1 = m + TPP + h;
+            const pk2 wxm = pk(ts.lx[d0], ts.lx[d1]), wym = pk(ts.ly[d0], ts.ly[d1]), wzm = pk(ts.lz[d0], ts.lz[d1]);
+            DirL2 dr;
+            dir_fwd_local2(dr, px, pl, wxm, wym, wzm);
+            float sp_lo, sp_hi;
+            upk(dr.spec, sp_lo, sp_hi);
+            float part[2 * TPP];
 #pragma unroll
-            for (int j = 0; j < TPP; ++j) {   // phase 1: arguments + exponentials of all TPP directions (TPP*3 independent chains)
-                const int d = m + j;
-                const float wx = tab.lx[d], wy = tab.ly[d], wz = tab.lz[d];
-                spec[j] = __shfl_sync(0xffffffffu, dr.spec, lane_base + j);
-                lobe_exps_pk<kLPT>(Lp, pk(wx, wx), pk(wy, wy), pk(wz, wz), arg[j], e[j]);
-            }
+            for (int half = 0; half < 2; ++half) {   // the two direction groups in turn: keeps only TPP*3 (arg, e) pairs live
+                pk2 arg[TPP][kLPT / 2], e[TPP][kLPT / 2];
+                float spec[TPP];
 #pragma unroll
-            for (int j = 0; j < TPP; ++j) {   // phase 2: accumulations
-                const int d = m + j;
-                const float wx = tab.lx[d], wy = tab.ly[d], wz = tab.lz[d];
-                part[j] = lobes_bwd_acc_pk<kLPT, PIX, LOBE>(g2, P2, Q2, arg[j], e[j], wx, wy, wz, tab.w[d] * wz, spec[j]);
+                for (int j = 0; j < TPP; ++j) {   // phase 1: arguments + exponentials
+                    const int d = m + half * TPP + j;
+                    const float wx = tab.lx[d], wy = tab.ly[d], wz = tab.lz[d];
+                    spec[j] = __shfl_sync(0xffffffffu, half ? sp_hi : sp_lo, lane_base + j);
+                    lobe_exps_pk<kLPT>(Lp, pk(wx, wx), pk(wy, wy), pk(wz, wz), arg[j], e[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < TPP; ++j) {   // phase 2: accumulations
+                    const int d = m + half * TPP + j;
+                    const float wx = tab.lx[d], wy = tab.ly[d], wz = tab.lz[d];
+                    part[half * TPP + j] =
+                        lobes_bwd_acc_pk<kLPT, PIX, LOBE>(g2, P2, Q2, arg[j], e[j], wx, wy, wz, tab.w[d] * wz, spec[j]);
+                }
             }
             if (PIX) {
-                const float sQm = grp_reduce_scatter<TPP>(part, h);
-                dir_bwd_local(gl, px, pl, dr, wxm, wym, wzm, ts.w[dm] * wzm * sQm);
+                float pa[TPP], pb[TPP];
+#pragma unroll
+                for (int j = 0; j < TPP; ++j) {
+                    pa[j] = part[j];
+                    pb[j] = part[TPP + j];
+                }
+                const float s0 = grp_reduce_scatter<TPP>(pa, h), s1 = grp_reduce_scatter<TPP>(pb, h);
+                float z0, z1;
+                upk(wzm, z0, z1);
+                dir_bwd_local2(gl2, px, pl, dr, wxm, wym, wzm, pk(ts.w[d0] * z0 * s0, ts.w[d1] * z1 * s1));
             }
         }
+        pixel_gradl2_fold(gl, gl2);
         gradspk_unpack<kLPT>(lg, g2);
     }
     // epilogue: outputs are predicated per thread by nulling the pointers of inactive threads
