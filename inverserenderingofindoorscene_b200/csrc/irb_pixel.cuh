@@ -104,11 +104,7 @@ template <int KC> __device__ __forceinline__ void pack_lobes(LobesPk<KC>& Lp, co
 template <int KC>
 __device__ __forceinline__ void lobe_exps_pk(const LobesPk<KC>& Lp, pk2 wx2, pk2 wy2, pk2 wz2, pk2 (&arg)[KC / 2], pk2 (&e)[KC / 2]) {
 #pragma unroll
-    for (int i = 0; i < KC / 2; ++i) arg[i] = fma2(Lp.bz[i], wz2, Lp.nlam[i]);
-#pragma unroll
-    for (int i = 0; i < KC / 2; ++i) arg[i] = fma2(Lp.by[i], wy2, arg[i]);
-#pragma unroll
-    for (int i = 0; i < KC / 2; ++i) arg[i] = fma2(Lp.bx[i], wx2, arg[i]);
+    for (int i = 0; i < KC / 2; ++i) arg[i] = fma2(Lp.bx[i], wx2, fma2(Lp.by[i], wy2, fma2(Lp.bz[i], wz2, Lp.nlam[i])));
 #pragma unroll
     for (int i = 0; i < KC / 2; ++i) e[i] = ex2x2(arg[i]);
 }
@@ -141,47 +137,31 @@ __device__ __forceinline__ float lobes_bwd_dir_pk(LobeGradsPk<KC>& g, const Lobe
     upk(sQ2, a, b);
     return a + b;
 }
-// accumulation phase only (arguments / exponentials precomputed by lobe_exps_pk), written stage by stage across the
-// lobe pairs so that independent instructions are adjacent in program order (ncu: the per-pair chains
-// e -> ew -> t -> {S, m} otherwise issue back to back and every instruction waits out the previous one's latency)
+// accumulation phase only (arguments / exponentials precomputed by lobe_exps_pk)
 template <int KC, bool PIX, bool LOBE>
 __device__ __forceinline__ float lobes_bwd_acc_pk(LobeGradsPk<KC>& g, const pk2 (&P2)[KC / 2], const pk2 (&Q2)[KC / 2],
                                                   const pk2 (&arg)[KC / 2], const pk2 (&e)[KC / 2], float wx, float wy, float wz,
                                                   float w, float spec) {
-    constexpr int N = KC / 2;
     const pk2 wx2 = pk(wx, wx), wy2 = pk(wy, wy), wz2 = pk(wz, wz);
     const pk2 w2 = pk(w, w), sp2 = pk(spec, spec);
-    float sQ = 0.f;
-    if (PIX) {
-        pk2 sQ2 = mul2(Q2[0], e[0]);
+    pk2 sQ2 = pk(0.f, 0.f);
 #pragma unroll
-        for (int i = 1; i < N; ++i) sQ2 = fma2(Q2[i], e[i], sQ2);
-        float a, b;
-        upk(sQ2, a, b);
-        sQ = a + b;
+    for (int i = 0; i < KC / 2; ++i) {
+        if (PIX) sQ2 = fma2(Q2[i], e[i], sQ2);
+        if (LOBE) {
+            const pk2 ew = mul2(e[i], w2);
+            g.U[i] = add2(g.U[i], ew);
+            g.V[i] = fma2(ew, sp2, g.V[i]);
+            const pk2 t = mul2(ew, fma2(sp2, Q2[i], P2[i]));
+            g.S[i] = fma2(t, arg[i], g.S[i]);
+            g.mx[i] = fma2(t, wx2, g.mx[i]);
+            g.my[i] = fma2(t, wy2, g.my[i]);
+            g.mz[i] = fma2(t, wz2, g.mz[i]);
+        }
     }
-    if (LOBE) {
-        pk2 ew[N], t[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) ew[i] = mul2(e[i], w2);
-#pragma unroll
-        for (int i = 0; i < N; ++i) t[i] = fma2(sp2, Q2[i], P2[i]);
-#pragma unroll
-        for (int i = 0; i < N; ++i) t[i] = mul2(ew[i], t[i]);
-#pragma unroll
-        for (int i = 0; i < N; ++i) g.U[i] = add2(g.U[i], ew[i]);
-#pragma unroll
-        for (int i = 0; i < N; ++i) g.V[i] = fma2(ew[i], sp2, g.V[i]);
-#pragma unroll
-        for (int i = 0; i < N; ++i) g.S[i] = fma2(t[i], arg[i], g.S[i]);
-#pragma unroll
-        for (int i = 0; i < N; ++i) g.mx[i] = fma2(t[i], wx2, g.mx[i]);
-#pragma unroll
-        for (int i = 0; i < N; ++i) g.my[i] = fma2(t[i], wy2, g.my[i]);
-#pragma unroll
-        for (int i = 0; i < N; ++i) g.mz[i] = fma2(t[i], wz2, g.mz[i]);
-    }
-    return sQ;
+    float a, b;
+    upk(sQ2, a, b);
+    return a + b;
 }
 template <int KC> __device__ __forceinline__ void gradspk_zero(LobeGradsPk<KC>& g) {
 #pragma unroll
