@@ -7,7 +7,11 @@
 // drop-ins for callers that hand forwardEnv an arbitrary env tensor; the fused kernel in
 // irb_render_sg.cu is the fast path when the env-map comes from SG lobes.
 #include "irb_common.cuh"
+#include <stdlib.h>
+
 #include "irb_driver_env.cuh"
+#include "irb_tma.cuh"
+#include "irb_sg_env_group.cuh"
 
 namespace irb {
 
@@ -36,6 +40,46 @@ __global__ void __launch_bounds__(kThreadsEnv) render_env_bwd_kernel(const Rende
     drv_render_env_bwd<float>(s, tab, blockIdx.y, pix);
 }
 
+// persistent TMA-staged lobe-split launch (irb_sg_env_group.cuh); falls back to the plain kernels when a plane is not
+// 16-byte addressable, when K > 24, or with IRB_SGENV_VARIANT=plain
+template <typename KernelT>
+static int launch_sg_group(KernelT kernel, const SgEnvArgs& s, const EnvTab& tab, int tile, cudaStream_t st, const char* what) {
+    const size_t plane = (size_t)s.R * s.C;
+    const size_t tiles_per_img = (plane + tile - 1) / tile;
+    const size_t total = tiles_per_img * (size_t)s.B;
+    const size_t smem = 2 * (size_t)(7 * s.K) * tile * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", what, smem, cudaGetErrorString(e));
+        return (int)e;
+    }
+    int per_sm = 1, dev = 0, sms = 148;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, smem);
+    if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    size_t grid = (size_t)sms * per_sm;
+    if (grid > total) grid = total;
+    if (const char* cap = getenv("IRB_TMA_MAX_CTAS")) {
+        const long c = atol(cap);
+        if (c > 0 && (size_t)c < grid) grid = (size_t)c;
+    }
+    kernel<<<(unsigned)grid, 128, smem, st>>>(s, tab, (unsigned)total, (unsigned)tiles_per_img);
+    return check_launch(what);
+}
+
+static bool sg_group_ok(const SgEnvArgs& s, const void* extra) {
+    const char* v = getenv("IRB_SGENV_VARIANT");
+    if (v && v[0] == 'p') return false;
+    if (s.K > 24) return false;
+    const size_t plane = (size_t)s.R * s.C;
+    if (plane % 4 != 0 || plane * (size_t)s.B >= 0xffffffffull) return false;
+    const void* ptrs[] = {s.axis, s.lamb, s.weight, extra};
+    for (const void* p : ptrs)
+        if (((uintptr_t)p & 15u) != 0) return false;
+    return true;
+}
+
 static int mk_tab(EnvTab& tab, int envH, int envW, int B, const char* who) {
     if (!make_env_tab(tab, envH, envW)) {
         set_error("%s: env table %dx%d unsupported (need envH*envW <= %d, multiple of 4)", who, envH, envW, IRB_MAX_DIRS);
@@ -61,6 +105,13 @@ extern "C" int irb_sg_to_env_fwd(const float* axis, const float* lamb, const flo
     SgEnvArgs s{};
     s.axis = axis; s.lamb = lamb; s.weight = weight; s.env = env; s.lamb_w = lamb_w; s.weight_w = weight_w;
     s.B = B; s.K = K; s.R = R; s.C = C; s.warp = warp;
+    if (sg_group_ok(s, env)) {
+        cudaStream_t st = (cudaStream_t)stream;
+        const char* w = "sg_to_env_fwd(group)";
+        if (K <= 6) return launch_sg_group(sg_env_group_kernel<0, 1>, s, tab, 128, st, w);
+        if (K <= 12) return launch_sg_group(sg_env_group_kernel<0, 2>, s, tab, 64, st, w);
+        return launch_sg_group(sg_env_group_kernel<0, 4>, s, tab, 32, st, w);
+    }
     const dim3 grid((unsigned)(((size_t)R * C + kThreadsEnv - 1) / kThreadsEnv), (unsigned)B);
     sg_to_env_fwd_kernel<12><<<grid, kThreadsEnv, 0, (cudaStream_t)stream>>>(s, tab);
     return check_launch("sg_to_env_fwd");
@@ -77,6 +128,13 @@ extern "C" int irb_sg_to_env_bwd(const float* axis, const float* lamb, const flo
     s.axis = axis; s.lamb = lamb; s.weight = weight; s.g_env = g_env;
     s.g_axis = g_axis; s.g_lamb = g_lamb; s.g_weight = g_weight;
     s.B = B; s.K = K; s.R = R; s.C = C; s.warp = warp;
+    if (sg_group_ok(s, g_env)) {
+        cudaStream_t st = (cudaStream_t)stream;
+        const char* w = "sg_to_env_bwd(group)";
+        if (K <= 6) return launch_sg_group(sg_env_group_kernel<1, 1>, s, tab, 128, st, w);
+        if (K <= 12) return launch_sg_group(sg_env_group_kernel<1, 2>, s, tab, 64, st, w);
+        return launch_sg_group(sg_env_group_kernel<1, 4>, s, tab, 32, st, w);
+    }
     const dim3 grid((unsigned)(((size_t)R * C + kThreadsEnv - 1) / kThreadsEnv), (unsigned)B);
     sg_to_env_bwd_kernel<12><<<grid, kThreadsEnv, 0, (cudaStream_t)stream>>>(s, tab);
     return check_launch("sg_to_env_bwd");

@@ -23,6 +23,7 @@
 
 #include "irb_common.cuh"
 #include "irb_driver.cuh"
+#include "irb_tma.cuh"
 
 namespace irb {
 
@@ -44,34 +45,6 @@ __global__ void __launch_bounds__(kThreads) render_sg_bwd_kernel(const RenderSgA
     const size_t pix = (size_t)blockIdx.x * kThreads + threadIdx.x;
     if (pix >= (size_t)a.R * a.C) return;
     drv_render_sg_bwd<float, KP, KL, PIX, LOBE>(a, tab, blockIdx.y, pix);
-}
-
-// ---------------------------------------------------------------------------------------------
-// TMA / mbarrier primitives (PTX; SASS: UBLKCP, SYNCS)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t ok = 0;
-    for (uint32_t spin = 0; !ok; ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (!ok && spin > (1u << 26)) __trap();  // a lost copy must fail the launch, never hang the GPU
-    }
 }
 
 // plane order inside a stage (each plane = kTile floats): albedo 3 | normal 3 | rough 1 | view 3 |

@@ -17,28 +17,6 @@
 
 namespace irb {
 
-template <int TPP> __device__ __forceinline__ float grp_allreduce(float v) {
-#pragma unroll
-    for (int o = 1; o < TPP; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// p[j] = this lane's partial for the direction owned by group member j; returns sum over members of p[h]
-template <int TPP> __device__ __forceinline__ float grp_reduce_scatter(const float (&p)[TPP], int h) {
-    if (TPP == 1) return p[0];
-    if (TPP == 2) {
-        const float send = h ? p[0] : p[1 % TPP];
-        const float keep = h ? p[1 % TPP] : p[0];
-        return keep + __shfl_xor_sync(0xffffffffu, send, 1);
-    }
-    // TPP == 4
-    const bool hi = (h & 2) != 0;
-    const float a0 = (hi ? p[2 % TPP] : p[0]) + __shfl_xor_sync(0xffffffffu, hi ? p[0] : p[2 % TPP], 2);
-    const float a1 = (hi ? p[3 % TPP] : p[1 % TPP]) + __shfl_xor_sync(0xffffffffu, hi ? p[1 % TPP] : p[3 % TPP], 2);
-    const bool odd = (h & 1) != 0;
-    return (odd ? a1 : a0) + __shfl_xor_sync(0xffffffffu, odd ? a0 : a1, 1);
-}
-
 __device__ __forceinline__ void issue_tile_n(float* stage, uint64_t* bar, const RenderSgArgs& a, size_t tile, size_t tiles_per_img,
                                              bool bwd, int PT) {
     const int lane = threadIdx.x & 31;
@@ -85,7 +63,6 @@ struct TabS {
     float lx[IRB_MAX_DIRS], ly[IRB_MAX_DIRS], lz[IRB_MAX_DIRS], w[IRB_MAX_DIRS];
 };
 
-constexpr int kLPT = 6;
 
 // ---- one tile, forward ----------------------------------------------------------------------
 template <int TPP>
