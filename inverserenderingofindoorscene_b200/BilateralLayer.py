@@ -116,44 +116,42 @@ class BilateralLayer(nn.Module):
         self.grid_params_arr.requires_grad = False
         self.bs_params_arr.requires_grad = False
 
-        # confidence network: 2 strided convs down, 2 convs up with a skip (BilateralLayer.py:211-232)
+        # confidence network (BilateralLayer.py:211-232): two stride-2 4x4 convs down, two 3x3 convs up with a skip
+        # connection, GroupNorm(2) after each, one 3x3 head.  Attribute names are the reference's so that its
+        # checkpoints (state_dict keys conv1, gn1, ..., dconvFinal) load unchanged.
         in_ch = 4 if mode in (2, 4) else 6
-        self.pad1 = nn.ReplicationPad2d(1)
-        self.conv1 = nn.Conv2d(in_channels=in_ch, out_channels=16, kernel_size=4, stride=2, bias=True)
-        self.gn1 = nn.GroupNorm(num_groups=2, num_channels=16)
-        self.pad2 = nn.ReplicationPad2d(1)
-        self.conv2 = nn.Conv2d(in_channels=16, out_channels=16, kernel_size=4, stride=2, bias=True)
-        self.gn2 = nn.GroupNorm(num_groups=2, num_channels=16)
-        self.dconv1 = nn.Conv2d(in_channels=16, out_channels=16, kernel_size=3, stride=1, padding=1, bias=True)
-        self.dgn1 = nn.GroupNorm(num_groups=2, num_channels=16)
-        self.dconv2 = nn.Conv2d(in_channels=32, out_channels=16, kernel_size=3, stride=1, padding=1, bias=True)
-        self.dgn2 = nn.GroupNorm(num_groups=2, num_channels=16)
-        self.dpad3 = nn.ReplicationPad2d(1)
-        self.dconvFinal = nn.Conv2d(in_channels=16, out_channels=1, kernel_size=3, stride=1, bias=True)
+        specs = (('conv1', in_ch, 16, 4, 2, 0), ('conv2', 16, 16, 4, 2, 0), ('dconv1', 16, 16, 3, 1, 1),
+                 ('dconv2', 32, 16, 3, 1, 1), ('dconvFinal', 16, 1, 3, 1, 0))
+        for name, cin, cout, ksz, stride, pad in specs:
+            setattr(self, name, nn.Conv2d(cin, cout, kernel_size=ksz, stride=stride, padding=pad, bias=True))
+        for name in ('gn1', 'gn2', 'dgn1', 'dgn2'):
+            setattr(self, name, nn.GroupNorm(num_groups=2, num_channels=16))
+        for name in ('pad1', 'pad2', 'dpad3'):
+            setattr(self, name, nn.ReplicationPad2d(1))
 
     def computePadding(self, os, ns):
         assert os <= ns
         gap = ns - os
-        return [int((gap + 1) / 2), int((gap - 1) / 2)] if gap % 2 else [int(gap / 2), int(gap / 2)]
+        return [(gap + 1) // 2, (gap - 1) // 2] if gap % 2 else [gap // 2, gap // 2]
 
     @staticmethod
     def _unit_scale(x):
         # per-sample max over (C,H,W), clamped to [1e-5, 1]  (BilateralLayer.py:244-254)
-        s = torch.clamp(x.amax(dim=(1, 2, 3), keepdim=True), 1e-5, 1)
-        return x / s
+        return x / torch.clamp(x.amax(dim=(1, 2, 3), keepdim=True), 1e-5, 1)
+
+    def _confidence(self, guide, pred):
+        """conf in (0,1], normalised by its batch maximum (BilateralLayer.py:256-270)."""
+        z = torch.cat([guide, pred], dim=1).detach()
+        block = lambda conv, gn, t: F.relu(gn(conv(t)), True)
+        e1 = block(self.conv1, self.gn1, self.pad1(z))
+        e2 = block(self.conv2, self.gn2, self.pad2(e1))
+        u1 = F.interpolate(block(self.dconv1, self.dgn1, e2), e1.shape[2:], mode='bilinear')
+        u2 = F.interpolate(block(self.dconv2, self.dgn2, torch.cat([u1, e1], dim=1)), z.shape[2:], mode='bilinear')
+        conf = 0.5 * (torch.tanh(self.dconvFinal(self.dpad3(u2))) + 1)
+        return conf / torch.clamp(conf.max(), min=1e-5)
 
     def forward(self, image, feature, pred):
         image = self._unit_scale(image)
         feature = self._unit_scale(feature)
-        inputBatch = torch.cat([image, pred], dim=1).detach()
-
-        x1 = F.relu(self.gn1(self.conv1(self.pad1(inputBatch))), True)
-        x2 = F.relu(self.gn2(self.conv2(self.pad2(x1))), True)
-        dx1 = F.relu(self.dgn1(self.dconv1(x2)), True)
-        dx1 = F.interpolate(dx1, [x1.size(2), x1.size(3)], mode='bilinear')
-        dx2 = F.relu(self.dgn2(self.dconv2(torch.cat([dx1, x1], dim=1))), True)
-        dx2 = F.interpolate(dx2, [inputBatch.size(2), inputBatch.size(3)], mode='bilinear')
-        conf = 0.5 * (torch.tanh(self.dconvFinal(self.dpad3(dx2))) + 1)
-        conf = conf / torch.clamp(conf.max(), min=1e-5)
-
+        conf = self._confidence(image, pred)
         return BilateralFunction.apply(feature.detach(), pred, conf, self.grid_params_arr, self.bs_params_arr)
