@@ -101,6 +101,19 @@ int irb_avgpool_fwd(const float* in, float* out, int N, int H, int W, int R, int
 int irb_avgpool_bwd(const float* g_out, float* g_in, int N, int H, int W, int R, int C, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Fused scale-ambiguity regression.  Replaces models.LSregressDiffSpec (models.py:23-84) for the
+ * reference's call pattern (wrapperBRDFLight.py:197-201: the statistics come from detached tensors):
+ * mask = im < 0.9; per-sample 2x2 normal equations on (diff, spec) -> (cD, cS) with the
+ * diffuse-only fallback and clamps of models.py:44-64; second scalar regression cI of
+ * clamp(cD diff + cS spec, 0, 1) onto im (models.py:70-78);
+ * out_diff = cI cD diff_orig, out_spec = cI cS spec_orig; coef[B,2] = (cI cD, cI cS) for the backward.
+ * All image pointers [B, n_per_sample]; stats = caller scratch of 8*B doubles.
+ * ------------------------------------------------------------------------------------- */
+int irb_lsregress_diffspec(const float* diff, const float* spec, const float* im, const float* diff_orig,
+                           const float* spec_orig, float* out_diff, float* out_spec, float* coef, double* stats,
+                           int B, long long n_per_sample, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Bilateral-grid solver.  Replaces BilateralGrid.BilateralGrid / bistochastize /
  * BilateralSolver.solve / solveGrad (BilateralGrid.py:44-207) and the per-image bridge
  * BilateralLayer.BilateralFunction.forward/backward (BilateralLayer.py:24-124).

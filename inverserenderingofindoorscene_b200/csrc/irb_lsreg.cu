@@ -1,0 +1,113 @@
+// irb_lsreg.cu -- fused scale-ambiguity regression of the rendered diffuse / specular images onto the photo
+// (models.LSregressDiffSpec, models.py:23-84).  The reference runs ~30 small PyTorch kernels
+// (masking, five per-sample reductions, clamps, a second regression on clamp(d+s,0,1)); here it is three launches:
+//   stats1 : per sample  a11 = sum (d m)^2, a22 = sum (s m)^2, a12 = sum d s m, b1 = sum d im m, b2 = sum s im m,  m = [im < 0.9]
+//   stats2 : per sample  sum r im, sum r^2 with r = clamp(cD d + cS s, 0, 1)   (cD, cS recomputed from stats1 by every block)
+//   apply  : out_d = cI cD d_orig, out_s = cI cS s_orig, and the per-sample coefficients (cI cD, cI cS) for the backward
+// Sums are accumulated per block in fp32 and across blocks in fp64 atomics.  The coefficients are constants of the
+// autograd graph exactly as in the reference's call pattern (its callers pass detached diff/spec, wrapperBRDFLight.py:197-201).
+#include "irb_common.cuh"
+
+namespace irb {
+
+__device__ __forceinline__ void block_sum_atomic(float v, double* dst) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v != 0.f) atomicAdd(dst, (double)v);
+}
+
+// coefficient logic of models.py:44-64 from the five sums
+__device__ __forceinline__ void ls_coefs(const double* st, double count, float& cD, float& cS) {
+    const double a11 = st[0], a22 = st[1], a12 = st[2], b1 = st[3], b2 = st[4];
+    const double frac = a11 * a22 - a12 * a12;
+    const double den = fmax(frac, 1e-2);
+    const double c1 = (b1 * a22 - b2 * a12) / den, c2 = (-b1 * a12 + a11 * b2) / den;
+    const double c3 = fmin(fmax(b1 / fmax(a11, 1e-5), 0.001), 1000.0);
+    const bool ok = (frac / count) > 1e-2;
+    cD = (float)fmin(fmax(ok ? c1 : c3, 0.0), 1000.0);
+    cS = (float)fmin(fmax(ok ? c2 : 0.0, 0.0), 1000.0);
+}
+
+__global__ void lsreg_stats1_kernel(const float* __restrict__ d, const float* __restrict__ s, const float* __restrict__ im,
+                                    double* __restrict__ stats, size_t n) {
+    const int b = blockIdx.y;
+    const float* dp = d + (size_t)b * n;
+    const float* sp = s + (size_t)b * n;
+    const float* ip = im + (size_t)b * n;
+    float a11 = 0, a22 = 0, a12 = 0, b1 = 0, b2 = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float iv = ip[i];
+        const float m = iv < 0.9f ? 1.f : 0.f;
+        const float dv = dp[i] * m, sv = sp[i] * m, imv = iv * m;
+        a11 += dv * dv;
+        a22 += sv * sv;
+        a12 += dv * sv;
+        b1 += dv * imv;
+        b2 += sv * imv;
+    }
+    double* st = stats + (size_t)b * 8;
+    block_sum_atomic(a11, st + 0);
+    block_sum_atomic(a22, st + 1);
+    block_sum_atomic(a12, st + 2);
+    block_sum_atomic(b1, st + 3);
+    block_sum_atomic(b2, st + 4);
+}
+
+__global__ void lsreg_stats2_kernel(const float* __restrict__ d, const float* __restrict__ s, const float* __restrict__ im,
+                                    double* __restrict__ stats, size_t n) {
+    const int b = blockIdx.y;
+    float cD, cS;
+    ls_coefs(stats + (size_t)b * 8, (double)n, cD, cS);
+    const float* dp = d + (size_t)b * n;
+    const float* sp = s + (size_t)b * n;
+    const float* ip = im + (size_t)b * n;
+    float ri = 0, rr = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float r = __saturatef(cD * dp[i] + cS * sp[i]);
+        ri += r * ip[i];
+        rr += r * r;
+    }
+    double* st = stats + (size_t)b * 8;
+    block_sum_atomic(ri, st + 5);
+    block_sum_atomic(rr, st + 6);
+}
+
+__global__ void lsreg_apply_kernel(const float* __restrict__ d, const float* __restrict__ s, const double* __restrict__ stats,
+                                   float* __restrict__ od, float* __restrict__ os, float* __restrict__ coef, size_t n) {
+    const int b = blockIdx.y;
+    float cD, cS;
+    const double* st = stats + (size_t)b * 8;
+    ls_coefs(st, (double)n, cD, cS);
+    const float cI = (float)fmin(fmax(st[5] / fmax(st[6], 1e-5), 0.001), 1000.0);
+    const float kd = cI * cD, ks = cI * cS;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        coef[2 * b] = kd;
+        coef[2 * b + 1] = ks;
+    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        od[(size_t)b * n + i] = kd * d[(size_t)b * n + i];
+        os[(size_t)b * n + i] = ks * s[(size_t)b * n + i];
+    }
+}
+
+}  // namespace irb
+
+using namespace irb;
+
+extern "C" int irb_lsregress_diffspec(const float* diff, const float* spec, const float* im, const float* diff_orig,
+                                      const float* spec_orig, float* out_diff, float* out_spec, float* coef, double* stats,
+                                      int B, long long n_per_sample, void* stream) {
+    IRB_REQUIRE(diff && spec && im && diff_orig && spec_orig && out_diff && out_spec && coef && stats, "lsregress_diffspec: null pointer");
+    IRB_REQUIRE(B > 0 && B <= 65535 && n_per_sample > 0, "lsregress_diffspec: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)n_per_sample;
+    cudaMemsetAsync(stats, 0, sizeof(double) * 8 * (size_t)B, st);
+    unsigned gx = (unsigned)((n + 256 * 8 - 1) / (256 * 8));
+    if (gx < 1) gx = 1;
+    if (gx > 1024) gx = 1024;
+    const dim3 grid(gx, (unsigned)B);
+    lsreg_stats1_kernel<<<grid, 256, 0, st>>>(diff, spec, im, stats, n);
+    lsreg_stats2_kernel<<<grid, 256, 0, st>>>(diff_orig, spec_orig, im, stats, n);  // models.py:66-72: on the scaled *Orig tensors
+    lsreg_apply_kernel<<<grid, 256, 0, st>>>(diff_orig, spec_orig, stats, out_diff, out_spec, coef, n);
+    return check_launch("lsregress_diffspec");
+}

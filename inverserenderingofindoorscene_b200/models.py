@@ -375,9 +375,51 @@ def LSregress(pred, gt, origin):
     return origin * coef.view([nb] + [1] * (origin.dim() - 1))
 
 
+class _LSregressDiffSpecFused(torch.autograd.Function):
+    """irb_lsregress_diffspec: three launches instead of ~30; coefficients are graph constants (models.py:58,76 detach)."""
+
+    @staticmethod
+    def forward(ctx, diff, spec, im, diffOrig, specOrig):
+        diff, spec, im = _c(diff), _c(spec), _c(im)
+        dO, sO = _c(diffOrig), _c(specOrig)
+        B = diff.shape[0]
+        n = diff.numel() // B
+        dev = diff.device
+        od, os_ = torch.empty_like(dO), torch.empty_like(sO)
+        coef = torch.empty(B, 2, device=dev, dtype=torch.float32)
+        stats = torch.empty(B, 8, device=dev, dtype=torch.float64)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().irb_lsregress_diffspec(
+                _lib.ptr(diff), _lib.ptr(spec), _lib.ptr(im), _lib.ptr(dO), _lib.ptr(sO), _lib.ptr(od), _lib.ptr(os_),
+                _lib.ptr(coef), _lib.ptr(stats), B, n, _lib.stream_ptr(dev)), 'irb_lsregress_diffspec')
+        ctx.save_for_backward(coef)
+        return od, os_
+
+    @staticmethod
+    def backward(ctx, g_d, g_s):
+        coef, = ctx.saved_tensors
+        B = coef.shape[0]
+        gd = g_d * coef[:, 0].view(B, 1, 1, 1) if (g_d is not None and ctx.needs_input_grad[3]) else None
+        gs = g_s * coef[:, 1].view(B, 1, 1, 1) if (g_s is not None and ctx.needs_input_grad[4]) else None
+        return None, None, None, gd, gs
+
+
 def LSregressDiffSpec(diff, spec, imOrig, diffOrig, specOrig):
     """Two-coefficient (diffuse, specular) per-sample regression with diffuse-only fallback, then a
-    second scalar fit of clamp(d+s,0,1) to the image (models.py:23-84)."""
+    second scalar fit of clamp(d+s,0,1) to the image (models.py:23-84).
+
+    CUDA float32 inputs whose statistics tensors (diff, spec, imOrig) carry no gradient -- the reference's
+    own call pattern, wrapperBRDFLight.py:197-201 -- take the fused kernel; anything else runs the
+    PyTorch expression of the same formula."""
+    if (diff.is_cuda and diff.dtype == torch.float32 and spec.dtype == torch.float32 and imOrig.dtype == torch.float32
+            and diffOrig.dtype == torch.float32 and specOrig.dtype == torch.float32 and diff.dim() == 4
+            and not (diff.requires_grad or spec.requires_grad or imOrig.requires_grad)
+            and diff.shape == spec.shape == imOrig.shape == diffOrig.shape == specOrig.shape):
+        return _LSregressDiffSpecFused.apply(diff, spec, imOrig, diffOrig, specOrig)
+    return _LSregressDiffSpec_torch(diff, spec, imOrig, diffOrig, specOrig)
+
+
+def _LSregressDiffSpec_torch(diff, spec, imOrig, diffOrig, specOrig):
     nb, nc, nh, nw = diff.size()
     mask = (imOrig < 0.9).float()
     d = (diff * mask).view(nb, -1)

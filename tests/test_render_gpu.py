@@ -376,3 +376,34 @@ def test_noncontiguous_and_needs_grad_subsets(irb):
     d3, s3 = rl.forwardSG(alb, nrm_g, rg, ax, lam, wt)
     (d3.sum() + s3.sum()).backward()
     assert nrm_g.grad is not None and torch.isfinite(nrm_g.grad).all()
+
+
+def test_lsregress_diffspec_fused(irb):
+    """fused irb_lsregress_diffspec against the PyTorch expression of models.py:23-84 and the reference fixture,
+    including the diffuse-only fallback branch and the gradient w.r.t. diffOrig / specOrig"""
+    from inverserenderingofindoorscene_b200.models import _LSregressDiffSpec_torch
+    dev = torch.device('cuda')
+    z = dict(np.load(os.path.join(GOLDEN, 'render_pool2_full.npz')))
+    d = torch.from_numpy(z['ref64_diff']).float().to(dev)
+    s = torch.from_numpy(z['ref64_spec']).float().to(dev)
+    im = torch.from_numpy(z['im']).to(dev)
+    dS, sS = irb.LSregressDiffSpec(d, s, im, d, s)
+    assert relerr(dS.cpu().numpy(), z['lsreg_diff']) <= 2e-5 and relerr(sS.cpu().numpy(), z['lsreg_spec']) <= 2e-5
+    g = torch.Generator(device='cuda').manual_seed(5)
+    for B, R, C, scale_spec in ((4, 120, 160, 1.0), (3, 17, 23, 1e-4), (2, 8, 8, 0.0)):
+        d = torch.rand(B, 3, R, C, device=dev, generator=g)
+        s = torch.rand(B, 3, R, C, device=dev, generator=g) * scale_spec   # tiny / zero spec -> diffuse-only fallback
+        im = torch.rand(B, 3, R, C, device=dev, generator=g) * 1.1
+        dO = d.clone().requires_grad_(True)
+        sO = s.clone().requires_grad_(True)
+        a1, a2 = irb.LSregressDiffSpec(d, s, im, dO, sO)
+        (a1.sum() + 2 * a2.sum()).backward()
+        dO2 = d.clone().requires_grad_(True)
+        sO2 = s.clone().requires_grad_(True)
+        b1, b2 = _LSregressDiffSpec_torch(d, s, im, dO2, sO2)
+        (b1.sum() + 2 * b2.sum()).backward()
+        assert relerr(a1.detach().cpu().numpy(), b1.detach().cpu().numpy()) <= 2e-5
+        if scale_spec > 0:
+            assert relerr(a2.detach().cpu().numpy(), b2.detach().cpu().numpy()) <= 2e-4
+        assert relerr(dO.grad.cpu().numpy(), dO2.grad.cpu().numpy()) <= 2e-5
+        assert relerr(sO.grad.cpu().numpy(), sO2.grad.cpu().numpy()) <= 2e-4
