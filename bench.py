@@ -409,7 +409,7 @@ def run_ours(args):
                        'global_batch': B * world, 'grid': [H, W], 'sg_lobes': K, 'parallelism': 'batch-shard x%d' % world,
                        'l2': 'inputs per step (447 MB/GPU) exceed the 126 MB L2; no explicit flush'},
             'kernel_ms': {'render_sg_fwd': fwd_ms, 'render_sg_bwd': bwd_ms},
-            'roofline': {'bound': 'hbm', 'kernel': 'render_sg_group_kernel<1,2,1,1,3> (fused backward, lobe-split)', 'achieved': ach,
+            'roofline': {'bound': 'hbm', 'kernel': 'render_sg_group_kernel<1,2,1,1,2> (fused backward, lobe-split)', 'achieved': ach,
                          'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': traffic_bwd,
                          'traffic_source': 'profiles/r01 ncu --set full capture (dram__bytes_read+write per launch)',
                          'peak_source': peak_src,
