@@ -175,7 +175,25 @@ __device__ __forceinline__ void group_tile_bwd(const RenderSgArgs& a, const Rend
             gDa[c] = gD[c] * A[c] * Consts<float>::INV_PI;
         }
         load_lobes(L, sv, vi.b, vi.pix, vi.plane, h * kLPT);
-        load_PQ<float, kLPT>(P, Q, sv, vi.b, vi.pix, vi.plane, h * kLPT, gDa, gS);
+        // P, Q from the warped intensities; the warped values overwrite the raw ones in this thread's own slots of the
+        // stage so that the epilogue (chain rule, d/dalbedo) does not evaluate the tan warp a second time
+        {
+            float* wst = const_cast<float*>(sv.weight);
+#pragma unroll
+            for (int k = 0; k < kLPT; ++k) {
+                P[k] = Q[k] = 0.f;
+                const int kk = h * kLPT + k;
+                if (kk < sv.K) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float w = load_weight<float>(sv, vi.b, vi.pix, vi.plane, kk, c);
+                        wst[(vi.b * (3 * sv.K) + 3 * kk + c) * vi.plane + vi.pix] = w;
+                        P[k] += gDa[c] * w;
+                        Q[k] += gS[c] * w;
+                    }
+                }
+            }
+        }
         LobesPk<kLPT> Lp;
         pack_lobes<kLPT>(Lp, L);
         pk2 P2[kLPT / 2], Q2[kLPT / 2];
@@ -231,7 +249,9 @@ __device__ __forceinline__ void group_tile_bwd(const RenderSgArgs& a, const Rend
     RenderSgArgs ao = a;
     if (!active) ao.g_axis = ao.g_lamb = ao.g_weight = nullptr;
     float gAlb[3] = {0.f, 0.f, 0.f};
-    if (LOBE) store_lobe_grads<float, kLPT>(lg, L, P, Q, sv, vi, ao, vo, h * kLPT, gDa, gS, gAlb);
+    RenderSgArgs svw = sv;   // stage view whose weight planes now hold WARPED values
+    svw.warp = 0;
+    if (LOBE) store_lobe_grads<float, kLPT>(lg, L, P, Q, svw, vi, ao, vo, h * kLPT, gDa, gS, gAlb);
     const size_t o3 = (vo.b * 3) * vo.plane + vo.pix;
     if (LOBE && a.g_albedo) {
 #pragma unroll
@@ -275,7 +295,7 @@ template <int MODE, int TPP, bool PIX, bool LOBE, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) render_sg_group_kernel(const RenderSgArgs a, const __grid_constant__ EnvTab tab,
                                                                           const unsigned total_tiles, const unsigned tiles_per_img) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[2];
+    __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2];
     __shared__ TabS ts;
     constexpr bool BWD = (MODE == 1);
     constexpr int PT = kThreads / TPP;
@@ -291,9 +311,14 @@ __global__ void __launch_bounds__(kThreads, MINB) render_sg_group_kernel(const R
     if (threadIdx.x == 0) {
         mbar_init(&full_bar[0], 1);
         mbar_init(&full_bar[1], 1);
+        mbar_init(&empty_bar[0], kThreads);
+        mbar_init(&empty_bar[1], kThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // Producer / consumer ring without block-wide barriers: warp 0 refills a stage as soon as all 128 threads have
+    // released it (empty barrier), the other warps never wait for each other, so the low-IPC per-tile prologue and
+    // epilogue of one warp overlap the direction sweeps of the others (ncu: 11 % barrier stalls with __syncthreads).
     const size_t plane = (size_t)a.R * a.C;
     const int q = threadIdx.x / TPP, h = threadIdx.x % TPP;
     unsigned t = blockIdx.x;
@@ -303,6 +328,8 @@ __global__ void __launch_bounds__(kThreads, MINB) render_sg_group_kernel(const R
         float* const cur = s ? stage1 : stage0;
         const unsigned tn = t + gridDim.x;
         if (tn < total_tiles && threadIdx.x < 32) {
+            const unsigned kfill = (it + 1) >> 1;            // fill index of stage s^1
+            if (kfill >= 1) mbar_wait(&empty_bar[s ^ 1], (kfill - 1) & 1);   // everyone finished the previous tenant
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue_tile_n(s ? stage0 : stage1, &full_bar[s ^ 1], a, tn, tiles_per_img, BWD, PT);
         }
@@ -314,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, MINB) render_sg_group_kernel(const R
         const PixView vo{b, pix0 + q, plane};
         if (MODE == 0) group_tile_fwd<TPP>(a, sv, tab, ts, vi, vo, in_range, h);
         else group_tile_bwd<TPP, PIX, LOBE>(a, sv, tab, ts, vi, vo, in_range, h);
-        __syncthreads();
+        mbar_arrive(&empty_bar[s]);   // this thread is done with stage s
     }
 }
 
