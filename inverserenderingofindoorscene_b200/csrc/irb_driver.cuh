@@ -61,7 +61,7 @@ IRB_HD void load_lobes(Lobes<T, KC>& L, const RenderSgArgs& a, size_t b, size_t 
 // sum_d T (a.w_d - 1) = a.M - N with N = sum_d T = P U + Q V.
 template <typename T>
 IRB_HD T lobe_lam_grad(T S, T lam, T mx, T my, T mz, T N, const float* axis, size_t oa, size_t plane) {
-    if (lam != T(0)) return S / lam;
+    if (lam != T(0)) return x_div(S, lam);
     return (T)axis[oa] * mx + (T)axis[oa + plane] * my + (T)axis[oa + 2 * plane] * mz - N;
 }
 

@@ -55,7 +55,15 @@ IRB_HD float x_rsqrt(float x) {
 #endif
 }
 IRB_HD double x_rsqrt(double x) { return 1.0 / sqrt(x); }
-IRB_HD float x_sqrt(float x) { return sqrtf(x); }
+IRB_HD float x_sqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;  // <= 1 ulp, no IEEE slow path (the once-per-pixel code was dominated by div/sqrt subroutine calls; profiles/r01)
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return sqrtf(x);
+#endif
+}
 IRB_HD double x_sqrt(double x) { return sqrt(x); }
 IRB_HD float x_rcp(float x) {
 #if defined(__CUDA_ARCH__)
@@ -67,6 +75,14 @@ IRB_HD float x_rcp(float x) {
 #endif
 }
 IRB_HD double x_rcp(double x) { return 1.0 / x; }
+// a / b: reciprocal-multiply on the device (<= 2 ulp), exact division on the host check
+template <typename T> IRB_HD T x_div(T a, T b) {
+#if defined(__CUDA_ARCH__)
+    return a * x_rcp(b);
+#else
+    return a / b;
+#endif
+}
 IRB_HD float x_mul(float a, float b) {
 #if defined(__CUDA_ARCH__)
     return __fmul_rn(a, b);
@@ -177,12 +193,12 @@ IRB_HD void pixel_setup(Pixel<T>& px, const V3<T>& nt, T rough, const V3<T>& v, 
     const T pl = x_sqrt(dot(p, p));
     px.p_ok = pl >= (T)1e-12;
     px.pn = x_max(pl, (T)1e-12);
-    px.camy = scale(T(1) / px.pn, p);
+    px.camy = scale(x_rcp(px.pn), p);
     const V3<T> q = cross(px.camy, px.n);
     const T ql = x_sqrt(dot(q, q));
     px.q_ok = ql >= (T)1e-12;
     px.qn = x_max(ql, (T)1e-12);
-    px.camx = scale(T(-1) / px.qn, q);
+    px.camx = scale(-x_rcp(px.qn), q);
     px.rho = (rough + T(1)) * T(0.5);
     px.k = (px.rho + T(1)) * (px.rho + T(1)) * T(0.125);
     const T a = px.rho * px.rho;
@@ -300,10 +316,10 @@ IRB_HD void pixel_bwd_finish(const PixelGrad<T>& g, const Pixel<T>& px, const V3
     V3<T> g_q;
     if (px.q_ok) {
         const T cg = dot(px.camx, g.g_cx);
-        g_q = V3<T>{-(g.g_cx.x - px.camx.x * cg) / px.qn, -(g.g_cx.y - px.camx.y * cg) / px.qn,
-                    -(g.g_cx.z - px.camx.z * cg) / px.qn};
+        const T iq = x_rcp(px.qn);
+        g_q = V3<T>{-(g.g_cx.x - px.camx.x * cg) * iq, -(g.g_cx.y - px.camx.y * cg) * iq, -(g.g_cx.z - px.camx.z * cg) * iq};
     } else {
-        g_q = scale(T(-1) / px.qn, g.g_cx);
+        g_q = scale(-x_rcp(px.qn), g.g_cx);
     }
     // q = camy x n
     const V3<T> t1 = cross(px.n, g_q);
@@ -314,9 +330,10 @@ IRB_HD void pixel_bwd_finish(const PixelGrad<T>& g, const Pixel<T>& px, const V3
     V3<T> g_p;
     if (px.p_ok) {
         const T cg = dot(px.camy, g_cy);
-        g_p = V3<T>{(g_cy.x - px.camy.x * cg) / px.pn, (g_cy.y - px.camy.y * cg) / px.pn, (g_cy.z - px.camy.z * cg) / px.pn};
+        const T ip = x_rcp(px.pn);
+        g_p = V3<T>{(g_cy.x - px.camy.x * cg) * ip, (g_cy.y - px.camy.y * cg) * ip, (g_cy.z - px.camy.z * cg) * ip};
     } else {
-        g_p = scale(T(1) / px.pn, g_cy);
+        g_p = scale(x_rcp(px.pn), g_cy);
     }
     // p = up - (up.n) n
     const T ngp = dot(px.n, g_p);
