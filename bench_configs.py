@@ -70,14 +70,20 @@ def run_trainlight(models, dev, iters):
     o2e = models.output2env(K, isCuda=True)
     im = torch.rand(B, 3, R, C, device=dev)
     envgt = torch.rand(B, 3, R, C, 8, 16, device=dev)
+    seg = (torch.rand(B, 1, R, C, device=dev) > 0.2).float()
+    segenv = seg.unsqueeze(-1).unsqueeze(-1)
 
-    def step():
+    def step():   # wrapperBRDFLight.py:177-207 with synthetic tensors
         a, l, w = [t.detach().requires_grad_(True) for t in (ax, lam, wt)]
         env, _, _, _ = o2e.output2env(a, l, w)
+        m = segenv.expand_as(envgt)
+        envs = models.LSregress(env.detach() * m, envgt * m, env)
+        dl = torch.log(envs + 1) - torch.log(envgt + 1)
+        rec = (dl * dl * m).sum() / (B * R * C) / 3.0 / 128
         d, s = rl.forwardEnv(alb, n, rg, env)
         dS, sS = models.LSregressDiffSpec(d.detach(), s.detach(), im, d, s)
-        rerr = ((torch.clamp(dS + sS, 0, 1) - im) ** 2).sum() / (B * R * C) / 3.0
-        rec = ((torch.log(env + 1) - torch.log(envgt + 1)) ** 2).sum() / (B * R * C) / 3.0 / 128
+        rend = torch.clamp(dS + sS, 0, 1)
+        rerr = ((rend - im) * (rend - im) * seg.expand_as(im)).sum() / (B * R * C) / 3.0
         (rerr + 10 * rec).backward()
     ms = timed(step, iters)
 

@@ -113,6 +113,12 @@ int irb_lsregress_diffspec(const float* diff, const float* spec, const float* im
                            const float* spec_orig, float* out_diff, float* out_spec, float* coef, double* stats,
                            int B, long long n_per_sample, void* stream);
 
+/* models.LSregress (models.py:7-21): coef[b] = clamp(sum(pred*gt)/clamp(sum(pred^2),1e-5), 1e-3, 1e3) per sample,
+ * out = origin * coef (coef is a constant of the autograd graph, models.py:13 .detach()).  pred / gt / origin / out
+ * [B, n_per_sample]; coef [B]; stats = caller scratch of 2*B doubles. */
+int irb_lsregress(const float* pred, const float* gt, const float* origin, float* out, float* coef, double* stats,
+                  int B, long long n_per_sample, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Bilateral-grid solver.  Replaces BilateralGrid.BilateralGrid / bistochastize /
  * BilateralSolver.solve / solveGrad (BilateralGrid.py:44-207) and the per-image bridge

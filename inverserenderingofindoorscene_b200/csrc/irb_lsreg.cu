@@ -6,6 +6,8 @@
 //   apply  : out_d = cI cD d_orig, out_s = cI cS s_orig, and the per-sample coefficients (cI cD, cI cS) for the backward
 // Sums are accumulated per block in fp32 and across blocks in fp64 atomics.  The coefficients are constants of the
 // autograd graph exactly as in the reference's call pattern (its callers pass detached diff/spec, wrapperBRDFLight.py:197-201).
+#include <stdint.h>
+
 #include "irb_common.cuh"
 
 namespace irb {
@@ -110,4 +112,78 @@ extern "C" int irb_lsregress_diffspec(const float* diff, const float* spec, cons
     lsreg_stats2_kernel<<<grid, 256, 0, st>>>(diff_orig, spec_orig, im, stats, n);  // models.py:66-72: on the scaled *Orig tensors
     lsreg_apply_kernel<<<grid, 256, 0, st>>>(diff_orig, spec_orig, stats, out_diff, out_spec, coef, n);
     return check_launch("lsregress_diffspec");
+}
+
+// ---------------------------------------------------------------------------------------------
+// models.LSregress (models.py:7-21): per-sample coef = clamp(sum(p g) / clamp(sum(p p), 1e-5), 1e-3, 1e3) (detached),
+// out = origin * coef.  Used on the 472 MB env-map for reconstErr (wrapperBRDFLight.py:180-181): two streaming passes
+// (16-byte loads, grid = multiple of the SM count) instead of ~9 tensor passes of PyTorch elementwise / reduce kernels.
+// ---------------------------------------------------------------------------------------------
+namespace irb {
+
+__global__ void lsreg_pg_kernel(const float* __restrict__ p, const float* __restrict__ g, double* __restrict__ stats, size_t n,
+                                int vec) {
+    const int b = blockIdx.y;
+    const float* pp = p + (size_t)b * n;
+    const float* gp = g + (size_t)b * n;
+    float pg = 0.f, pq = 0.f;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    if (vec) {
+        const float4* p4 = reinterpret_cast<const float4*>(pp);
+        const float4* g4 = reinterpret_cast<const float4*>(gp);
+        for (size_t i = tid; i < n / 4; i += nth) {
+            const float4 a = p4[i], c = g4[i];
+            pg += a.x * c.x + a.y * c.y + a.z * c.z + a.w * c.w;
+            pq += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+        }
+    } else {
+        for (size_t i = tid; i < n; i += nth) {
+            pg += pp[i] * gp[i];
+            pq += pp[i] * pp[i];
+        }
+    }
+    block_sum_atomic(pg, stats + (size_t)b * 2);
+    block_sum_atomic(pq, stats + (size_t)b * 2 + 1);
+}
+
+__global__ void lsreg_scale_kernel(const float* __restrict__ origin, const double* __restrict__ stats, float* __restrict__ out,
+                                   float* __restrict__ coef, size_t n, int vec) {
+    const int b = blockIdx.y;
+    const double* st = stats + (size_t)b * 2;
+    const float c = (float)fmin(fmax(st[0] / fmax(st[1], 1e-5), 0.001), 1000.0);
+    if (blockIdx.x == 0 && threadIdx.x == 0) coef[b] = c;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    if (vec) {
+        const float4* o4 = reinterpret_cast<const float4*>(origin + (size_t)b * n);
+        float4* d4 = reinterpret_cast<float4*>(out + (size_t)b * n);
+        for (size_t i = tid; i < n / 4; i += nth) {
+            float4 v = o4[i];
+            v.x *= c; v.y *= c; v.z *= c; v.w *= c;
+            d4[i] = v;
+        }
+    } else {
+        for (size_t i = tid; i < n; i += nth) out[(size_t)b * n + i] = c * origin[(size_t)b * n + i];
+    }
+}
+
+}  // namespace irb
+
+extern "C" int irb_lsregress(const float* pred, const float* gt, const float* origin, float* out, float* coef, double* stats,
+                             int B, long long n_per_sample, void* stream) {
+    IRB_REQUIRE(pred && gt && origin && out && coef && stats, "lsregress: null pointer");
+    IRB_REQUIRE(B > 0 && B <= 65535 && n_per_sample > 0, "lsregress: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)n_per_sample;
+    const int vec = (n % 4 == 0) && ((((uintptr_t)pred | (uintptr_t)gt | (uintptr_t)origin | (uintptr_t)out) & 15u) == 0);
+    cudaMemsetAsync(stats, 0, sizeof(double) * 2 * (size_t)B, st);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    size_t want = (n / (vec ? 4 : 1) + 256 * 4 - 1) / (256 * 4);
+    size_t cap = (size_t)sms * 8 / (size_t)B + 1;   // ~8 resident CTAs per SM over the whole batch
+    unsigned gx = (unsigned)(want < cap ? (want ? want : 1) : cap);
+    const dim3 grid(gx, (unsigned)B);
+    irb::lsreg_pg_kernel<<<grid, 256, 0, st>>>(pred, gt, stats, n, vec);
+    irb::lsreg_scale_kernel<<<grid, 256, 0, st>>>(origin, stats, out, coef, n, vec);
+    return irb::check_launch("lsregress");
 }

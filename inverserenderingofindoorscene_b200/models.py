@@ -365,8 +365,39 @@ class renderingLayer():
 # scale-ambiguity regressions (models.py:7-84) -- PyTorch (per-sample reductions)
 # ------------------------------------------------------------------------------------------
 
+class _LSregressFused(torch.autograd.Function):
+    """irb_lsregress: one streaming pass for the two sums, one for the scaling (models.py:7-21)."""
+
+    @staticmethod
+    def forward(ctx, pred, gt, origin):
+        pred, gt, origin = _c(pred), _c(gt), _c(origin)
+        B = pred.shape[0]
+        n = pred.numel() // B
+        dev = pred.device
+        out = torch.empty_like(origin)
+        coef = torch.empty(B, device=dev, dtype=torch.float32)
+        stats = torch.empty(B, 2, device=dev, dtype=torch.float64)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().irb_lsregress(_lib.ptr(pred), _lib.ptr(gt), _lib.ptr(origin), _lib.ptr(out), _lib.ptr(coef),
+                                                _lib.ptr(stats), B, n, _lib.stream_ptr(dev)), 'irb_lsregress')
+        ctx.save_for_backward(coef)
+        ctx.odim = origin.dim()
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        coef, = ctx.saved_tensors
+        return None, None, g * coef.view([-1] + [1] * (ctx.odim - 1))
+
+
 def LSregress(pred, gt, origin):
-    """Per-sample least-squares scale mapping pred onto gt, applied to origin (models.py:7-21)."""
+    """Per-sample least-squares scale mapping pred onto gt, applied to origin (models.py:7-21).
+
+    CUDA float32 tensors of one shape whose pred / gt carry no gradient (the reference's call pattern,
+    wrapperBRDFLight.py:180-181) take the fused kernels; anything else the PyTorch expression."""
+    if (pred.is_cuda and pred.dtype == gt.dtype == origin.dtype == torch.float32 and pred.shape == gt.shape == origin.shape
+            and pred.dim() >= 2 and not (pred.requires_grad or gt.requires_grad)):
+        return _LSregressFused.apply(pred, gt, origin)
     nb = pred.size(0)
     p = pred.reshape(nb, -1)
     g = gt.reshape(nb, -1)

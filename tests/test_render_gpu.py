@@ -407,3 +407,22 @@ def test_lsregress_diffspec_fused(irb):
             assert relerr(a2.detach().cpu().numpy(), b2.detach().cpu().numpy()) <= 2e-4
         assert relerr(dO.grad.cpu().numpy(), dO2.grad.cpu().numpy()) <= 2e-5
         assert relerr(sO.grad.cpu().numpy(), sO2.grad.cpu().numpy()) <= 2e-4
+
+
+def test_lsregress_fused(irb):
+    """fused irb_lsregress (two streaming passes) against the PyTorch expression of models.py:7-21, on an env-map
+    shaped tensor, a ragged one (scalar path) and with the clamps active; gradient w.r.t. origin"""
+    dev = torch.device('cuda')
+    g = torch.Generator(device='cuda').manual_seed(9)
+    for shape, scale in (((3, 3, 12, 16, 8, 16), 1.0), ((2, 3, 5, 7), 1.0), ((2, 1, 9, 9), 1e-5), ((2, 1, 8, 8), 1e4)):
+        pred = torch.rand(*shape, device=dev, generator=g) * scale
+        gt = torch.rand(*shape, device=dev, generator=g)
+        origin = pred.clone().requires_grad_(True)
+        out = irb.LSregress(pred, gt, origin)
+        out.sum().backward()
+        nb = shape[0]
+        coef = torch.clamp((pred.reshape(nb, -1) * gt.reshape(nb, -1)).sum(1) /
+                           torch.clamp((pred.reshape(nb, -1) ** 2).sum(1), min=1e-5), 0.001, 1000)
+        ref = pred * coef.view([nb] + [1] * (len(shape) - 1))
+        assert relerr(out.detach().cpu().numpy(), ref.cpu().numpy()) <= 2e-5
+        assert relerr(origin.grad.cpu().numpy(), coef.view([nb] + [1] * (len(shape) - 1)).expand(shape).cpu().numpy()) <= 2e-5
