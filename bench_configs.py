@@ -87,6 +87,22 @@ def run_trainlight(models, dev, iters):
         (rerr + 10 * rec).backward()
     ms = timed(step, iters)
 
+    def step_fused():   # same losses; reconstruction term through output2env.reconstLoss, render term through forwardSG
+        a, l, w = [t.detach().requires_grad_(True) for t in (ax, lam, wt)]
+        rec, _ = o2e.reconstLoss(a, l, w, envgt, segenv)
+        d, s = rl.forwardSG(alb, n, rg, a, l, w)
+        dS, sS = models.LSregressDiffSpec(d.detach(), s.detach(), im, d, s)
+        rend = torch.clamp(dS + sS, 0, 1)
+        rerr = ((rend - im) * (rend - im) * seg.expand_as(im)).sum() / (B * R * C) / 3.0
+        (rerr + 10 * rec).backward()
+    ms_f = timed(step_fused, iters)
+
+    def reconst_only():
+        a, l, w = [t.detach().requires_grad_(True) for t in (ax, lam, wt)]
+        rec, _ = o2e.reconstLoss(a, l, w, envgt, segenv)
+        rec.backward()
+    ms_rec = timed(reconst_only, iters)
+
     def render_only():
         a, l, w = [t.detach().requires_grad_(True) for t in (ax, lam, wt)]
         d, s = rl.forwardSG(alb, n, rg, a, l, w)
@@ -94,8 +110,11 @@ def run_trainlight(models, dev, iters):
     ms_r = timed(render_only, iters)
     npx = B * R * C
     return {'config': 'trainLight geometry: maps 16x240x320 -> grid 120x160, 12 SG', 'render_loss_step_ms': ms,
+            'render_loss_step_envfree_ms': ms_f, 'reconst_loss_fwd_bwd_ms': ms_rec,
             'fused_render_fwd_bwd_sg_grads_only_ms': ms_r, 'render_Mpix_s': npx / ms_r / 1e3,
-            'note': 'step = output2env (env materialised) + fused forwardEnv + LSregressDiffSpec + render/reconst losses + backward'}
+            'note': 'step = wrapperBRDFLight.py:177-207: output2env (env materialised) + masked LSregress + log-L2 + fused '
+                    'forwardEnv + LSregressDiffSpec + render loss + backward; envfree = the same losses with '
+                    'output2env.reconstLoss + forwardSG (the env-map is never written)'}
 
 
 def run_unfused(models, dev, iters):

@@ -119,6 +119,20 @@ int irb_lsregress_diffspec(const float* diff, const float* spec, const float* im
 int irb_lsregress(const float* pred, const float* gt, const float* origin, float* out, float* coef, double* stats,
                   int B, long long n_per_sample, void* stream);
 
+/* Fused reconstruction loss of the light branch: replaces, for an env-map that comes from SG lobes, the chain
+ *   envPred = output2env(axis, lamb, weight)                                   (wrapperBRDFLight.py:172)
+ *   envScaled = LSregress(envPred.detach()*seg, envGT*seg, envPred)            (wrapperBRDFLight.py:179-181)
+ *   num = sum((log(envScaled + off) - log(envGT + off))^2 * seg)               (wrapperBRDFLight.py:183-187)
+ * without materialising envPred.  env_gt [B,3,R,C,envH,envW]; seg [B,1,R,C] (mask or fractional weight);
+ * stats [B,4] fp64 out = {sum(E G s^2), sum(E^2 s^2), num_b, sum(s)}; coef_b = clamp(stats0/max(stats1,1e-5), 1e-3, 1e3).
+ * bwd: g_num = device scalar dL/d(sum_b num_b); writes the gradients w.r.t. the ORIGINAL SG parameters (coef is a
+ * graph constant as in models.py:13).  Needs K <= 24, R*C % 4 == 0, 16-byte aligned buffers (else IRB_E_UNSUPPORTED). */
+int irb_sg_reconst_fwd(const float* axis, const float* lamb, const float* weight, const float* env_gt, const float* seg,
+                       double* stats, int B, int K, int R, int C, int envH, int envW, int warp, float offset, void* stream);
+int irb_sg_reconst_bwd(const float* axis, const float* lamb, const float* weight, const float* env_gt, const float* seg,
+                       const double* stats, const float* g_num, float* g_axis, float* g_lamb, float* g_weight, int B, int K,
+                       int R, int C, int envH, int envW, int warp, float offset, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Bilateral-grid solver.  Replaces BilateralGrid.BilateralGrid / bistochastize /
  * BilateralSolver.solve / solveGrad (BilateralGrid.py:44-207) and the per-image bridge

@@ -40,6 +40,12 @@ struct SgEnvArgs {
     float* g_weight;
     int B, K, R, C;
     int warp;
+    // fused reconstruction loss (irb_sg_reconst_*; wrapperBRDFLight.py:179-188)
+    const float* env_gt;   // [B,3,R,C,D]
+    const float* seg;      // [B,1,R,C] mask / weight of the pixel
+    double* stats;         // [B,4]: sum(E G s^2), sum(E^2 s^2), sum((log(cE+off)-log(G+off))^2 s), sum(s)
+    const float* g_num;    // device scalar: dL/d(numerator)
+    float offset;
 };
 
 IRB_HD RenderSgArgs as_render_args(const SgEnvArgs& s) {

@@ -140,6 +140,68 @@ extern "C" int irb_sg_to_env_bwd(const float* axis, const float* lamb, const flo
     return check_launch("sg_to_env_bwd");
 }
 
+// Fused reconstruction loss of the light branch (wrapperBRDFLight.py:177-188): the predicted env-map is evaluated from
+// its SG lobes inside the kernels and compared with the ground truth on the fly, so the only large stream is the
+// ground-truth env-map (read once per pass).  stats[b] = {sum E G s^2, sum E^2 s^2, sum dlog^2 s, sum s} in fp64.
+extern "C" int irb_sg_reconst_fwd(const float* axis, const float* lamb, const float* weight, const float* env_gt,
+                                  const float* seg, double* stats, int B, int K, int R, int C, int envH, int envW, int warp,
+                                  float offset, void* stream) {
+    IRB_REQUIRE(B > 0 && K > 0 && R > 0 && C > 0, "sg_reconst_fwd: non-positive shape");
+    IRB_REQUIRE(axis && lamb && weight && env_gt && seg && stats, "sg_reconst_fwd: null pointer");
+    IRB_REQUIRE(offset > 0.f, "sg_reconst_fwd: offset must be positive");
+    EnvTab tab;
+    if (int rc = mk_tab(tab, envH, envW, B, "sg_reconst_fwd")) return rc;
+    SgEnvArgs s{};
+    s.axis = axis; s.lamb = lamb; s.weight = weight; s.env_gt = env_gt; s.seg = seg; s.stats = stats; s.offset = offset;
+    s.B = B; s.K = K; s.R = R; s.C = C; s.warp = warp;
+    if (!sg_group_ok(s, env_gt)) {
+        set_error("sg_reconst_fwd: needs K <= 24, R*C %% 4 == 0 and 16-byte aligned planes");
+        return IRB_E_UNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 4 * (size_t)B, st);
+    if (e != cudaSuccess) {
+        set_error("sg_reconst_fwd: memset: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    int rc;
+    if (K <= 6) {
+        rc = launch_sg_group(sg_env_group_kernel<2, 1>, s, tab, 128, st, "sg_reconst_fwd(stats)");
+        if (!rc) rc = launch_sg_group(sg_env_group_kernel<3, 1>, s, tab, 128, st, "sg_reconst_fwd(loss)");
+    } else if (K <= 12) {
+        rc = launch_sg_group(sg_env_group_kernel<2, 2>, s, tab, 64, st, "sg_reconst_fwd(stats)");
+        if (!rc) rc = launch_sg_group(sg_env_group_kernel<3, 2>, s, tab, 64, st, "sg_reconst_fwd(loss)");
+    } else {
+        rc = launch_sg_group(sg_env_group_kernel<2, 4>, s, tab, 32, st, "sg_reconst_fwd(stats)");
+        if (!rc) rc = launch_sg_group(sg_env_group_kernel<3, 4>, s, tab, 32, st, "sg_reconst_fwd(loss)");
+    }
+    return rc;
+}
+
+extern "C" int irb_sg_reconst_bwd(const float* axis, const float* lamb, const float* weight, const float* env_gt,
+                                  const float* seg, const double* stats, const float* g_num, float* g_axis, float* g_lamb,
+                                  float* g_weight, int B, int K, int R, int C, int envH, int envW, int warp, float offset,
+                                  void* stream) {
+    IRB_REQUIRE(B > 0 && K > 0 && R > 0 && C > 0, "sg_reconst_bwd: non-positive shape");
+    IRB_REQUIRE(axis && lamb && weight && env_gt && seg && stats && g_num, "sg_reconst_bwd: null pointer");
+    IRB_REQUIRE(offset > 0.f, "sg_reconst_bwd: offset must be positive");
+    EnvTab tab;
+    if (int rc = mk_tab(tab, envH, envW, B, "sg_reconst_bwd")) return rc;
+    SgEnvArgs s{};
+    s.axis = axis; s.lamb = lamb; s.weight = weight; s.env_gt = env_gt; s.seg = seg;
+    s.stats = const_cast<double*>(stats); s.g_num = g_num; s.offset = offset;
+    s.g_axis = g_axis; s.g_lamb = g_lamb; s.g_weight = g_weight;
+    s.B = B; s.K = K; s.R = R; s.C = C; s.warp = warp;
+    if (!sg_group_ok(s, env_gt)) {
+        set_error("sg_reconst_bwd: needs K <= 24, R*C %% 4 == 0 and 16-byte aligned planes");
+        return IRB_E_UNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (K <= 6) return launch_sg_group(sg_env_group_kernel<4, 1>, s, tab, 128, st, "sg_reconst_bwd");
+    if (K <= 12) return launch_sg_group(sg_env_group_kernel<4, 2>, s, tab, 64, st, "sg_reconst_bwd");
+    return launch_sg_group(sg_env_group_kernel<4, 4>, s, tab, 32, st, "sg_reconst_bwd");
+}
+
 extern "C" int irb_render_env_fwd(const float* albedo, const float* normal, const float* rough, const float* env,
                                   const float* view, float* out_diff, float* out_spec, int B, int R, int C, int envH,
                                   int envW, float F0, void* stream) {

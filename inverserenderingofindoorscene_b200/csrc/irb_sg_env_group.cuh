@@ -30,9 +30,27 @@ __device__ __forceinline__ void issue_sg_tile(float* stage, uint64_t* bar, const
     }
 }
 
-// MODE 0: forward (env, optional warped lamb / weight), MODE 1: backward
+// MODE 0: forward (env, optional warped lamb / weight), MODE 1: backward from a given env-map gradient,
+// MODE 2 / 3 / 4: fused reconstruction loss against a ground-truth env-map WITHOUT materialising the predicted one
+//   2: per-sample regression sums  sum(E G s^2), sum(E^2 s^2), sum(s)           (models.LSregress, models.py:7-21)
+//   3: numerator  sum((log(c E + off) - log(G + off))^2 s)                        (wrapperBRDFLight.py:183-187)
+//   4: its gradient w.r.t. the SG parameters (c is a graph constant, models.py:13)
+__device__ __forceinline__ void sg_block_add(float v, double* dst) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v != 0.f) atomicAdd(dst, (double)v);
+}
+__device__ __forceinline__ float reconst_coef(const double* st) {
+    return (float)fmin(fmax(st[0] / fmax(st[1], 1e-5), 0.001), 1000.0);
+}
+__device__ __forceinline__ float fast_log(float x) {   // natural log via lg2.approx (abs err ~1e-7 for x >= offset > 0)
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y * 0.69314718055994530942f;
+}
+
 template <int MODE, int TPP>
-__global__ void __launch_bounds__(128, (MODE == 0 ? 4 : 3)) sg_env_group_kernel(const SgEnvArgs s, const __grid_constant__ EnvTab tab,
+__global__ void __launch_bounds__(128, ((MODE == 1 || MODE == 4) ? 3 : 4)) sg_env_group_kernel(const SgEnvArgs s, const __grid_constant__ EnvTab tab,
                                                               const unsigned total_tiles, const unsigned tiles_per_img) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[2];
@@ -85,8 +103,8 @@ __global__ void __launch_bounds__(128, (MODE == 0 ? 4 : 3)) sg_env_group_kernel(
 #pragma unroll
             for (int i = 0; i < NP2; ++i) W2[c][i] = pk(W[2 * i][c], W[2 * i + 1][c]);
 
-        if (MODE == 0) {
-            if (active && (s.lamb_w || s.weight_w)) {
+        if (MODE == 0 || MODE == 2 || MODE == 3) {
+            if (MODE == 0 && active && (s.lamb_w || s.weight_w)) {
 #pragma unroll
                 for (int k = 0; k < kLPT; ++k) {
                     const int kk = h * kLPT + k;
@@ -98,6 +116,9 @@ __global__ void __launch_bounds__(128, (MODE == 0 ? 4 : 3)) sg_env_group_kernel(
                     }
                 }
             }
+            const float sg = (MODE != 0 && active) ? s.seg[b * plane + pix] : 0.f;
+            const float coef = (MODE == 3) ? reconst_coef(s.stats + b * 4) : 1.f;
+            float acc0 = 0.f, acc1 = 0.f;   // MODE 2: sum E G, sum E^2;  MODE 3: sum dlog^2
             for (int d0 = 0; d0 < D; d0 += 4) {
                 float E[3][4];
 #pragma unroll
@@ -113,11 +134,39 @@ __global__ void __launch_bounds__(128, (MODE == 0 ? 4 : 3)) sg_env_group_kernel(
                         E[c][u] = grp_allreduce<TPP>(hsum2(acc));
                     }
                 }
-                // the TPP lanes of a group share the stores: channel c of this 4-direction block goes to lane (c + d0/4) % TPP
+                // the TPP lanes of a group share the 16-byte accesses: channel c of this 4-direction block belongs to
+                // lane (c + d0/4) % TPP
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    if (active && ((c + (d0 >> 2)) % TPP) == h)
-                        st4(s.env + ((b * 3 + c) * plane + pix) * D + d0, E[c][0], E[c][1], E[c][2], E[c][3]);
+                    if (active && ((c + (d0 >> 2)) % TPP) == h) {
+                        if (MODE == 0) {
+                            st4(s.env + ((b * 3 + c) * plane + pix) * D + d0, E[c][0], E[c][1], E[c][2], E[c][3]);
+                        } else if (sg != 0.f) {
+                            const F4 g = ld4(s.env_gt + ((b * 3 + c) * plane + pix) * D + d0);
+                            const float G[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (MODE == 2) {
+                                    acc0 += E[c][u] * G[u];
+                                    acc1 += E[c][u] * E[c][u];
+                                } else {
+                                    const float dl = fast_log(coef * E[c][u] + s.offset) - fast_log(G[u] + s.offset);
+                                    acc0 += dl * dl;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (MODE != 0) {
+                // per-pixel weights: the regression sees (E s)(G s) and (E s)^2, the loss sees dlog^2 * s
+                double* st = s.stats + b * 4;
+                if (MODE == 2) {
+                    sg_block_add(acc0 * sg * sg, st + 0);
+                    sg_block_add(acc1 * sg * sg, st + 1);
+                    sg_block_add((h == 0) ? sg : 0.f, st + 3);
+                } else {
+                    sg_block_add(acc0 * sg, st + 2);
                 }
             }
         } else {
@@ -127,23 +176,38 @@ __global__ void __launch_bounds__(128, (MODE == 0 ? 4 : 3)) sg_env_group_kernel(
                 S2[i] = N2[i] = mx2[i] = my2[i] = mz2[i] = pk(0.f, 0.f);
                 gW2[0][i] = gW2[1][i] = gW2[2][i] = pk(0.f, 0.f);
             }
-            const float* gp0 = s.g_env + ((b * 3 + 0) * plane + pix) * D;
-            const float* gp1 = s.g_env + ((b * 3 + 1) * plane + pix) * D;
-            const float* gp2 = s.g_env + ((b * 3 + 2) * plane + pix) * D;
+            const float* gsrc = (MODE == 4) ? s.env_gt : s.g_env;
+            const float* gp0 = gsrc + ((b * 3 + 0) * plane + pix) * D;
+            const float* gp1 = gsrc + ((b * 3 + 1) * plane + pix) * D;
+            const float* gp2 = gsrc + ((b * 3 + 2) * plane + pix) * D;
+            const float sg4 = (MODE == 4 && active) ? s.seg[b * plane + pix] : 0.f;
+            const float coef4 = (MODE == 4) ? reconst_coef(s.stats + b * 4) : 1.f;
+            const float gfac = (MODE == 4) ? 2.f * coef4 * sg4 * s.g_num[0] : 0.f;
             F4 n0 = ld4(gp0), n1 = ld4(gp1), n2 = ld4(gp2);
             for (int d0 = 0; d0 < D; d0 += 4) {
                 const F4 g0 = n0, g1 = n1, g2 = n2;
-                if (d0 + 4 < D) {   // next block of the gradient stream, one block ahead of its use
+                if (d0 + 4 < D) {   // next block of the stream, one block ahead of its use
                     n0 = ld4(gp0 + d0 + 4);
                     n1 = ld4(gp1 + d0 + 4);
                     n2 = ld4(gp2 + d0 + 4);
                 }
-                const float G[3][4] = {{g0.x, g0.y, g0.z, g0.w}, {g1.x, g1.y, g1.z, g1.w}, {g2.x, g2.y, g2.z, g2.w}};
+                float G[3][4] = {{g0.x, g0.y, g0.z, g0.w}, {g1.x, g1.y, g1.z, g1.w}, {g2.x, g2.y, g2.z, g2.w}};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const float wx = tab.lx[d0 + u], wy = tab.ly[d0 + u], wz = tab.lz[d0 + u];
                     pk2 arg[NP2], e[NP2];
                     lobe_exps_pk<kLPT>(Lp, pk(wx, wx), pk(wy, wy), pk(wz, wz), arg, e);
+                    if (MODE == 4) {   // dL/dE_cd = g * 2 c s (log(cE+off) - log(G+off)) / (cE+off)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            pk2 acc = mul2(W2[c][0], e[0]);
+#pragma unroll
+                            for (int i = 1; i < NP2; ++i) acc = fma2(W2[c][i], e[i], acc);
+                            const float Ecd = grp_allreduce<TPP>(hsum2(acc));
+                            const float ce = coef4 * Ecd + s.offset;
+                            G[c][u] = gfac * (fast_log(ce) - fast_log(G[c][u] + s.offset)) * x_rcp(ce);
+                        }
+                    }
                     const pk2 G0 = pk(G[0][u], G[0][u]), G1 = pk(G[1][u], G[1][u]), G2 = pk(G[2][u], G[2][u]);
                     const pk2 wx2 = pk(wx, wx), wy2 = pk(wy, wy), wz2 = pk(wz, wz);
 #pragma unroll

@@ -127,6 +127,47 @@ class _SgToEnv(torch.autograd.Function):
         return g_axis, g_lamb, g_weight, None, None, None
 
 
+class _SgReconstLoss(torch.autograd.Function):
+    """sum((log(c*E(sg) + off) - log(envGT + off))^2 * seg) with c the per-sample LSregress scale, the env-map E never
+    leaving the kernels (wrapperBRDFLight.py:172-188).  Returns (numerator, sum(seg), coef[B])."""
+
+    @staticmethod
+    def forward(ctx, axis, lamb, weight, env_gt, seg, envH, envW, offset):
+        axis, lamb, weight, env_gt, seg = _c(axis), _c(lamb), _c(weight), _c(env_gt), _c(seg)
+        B, K, _, R, C = axis.shape
+        dev = axis.device
+        stats = torch.empty(B, 4, device=dev, dtype=torch.float64)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().irb_sg_reconst_fwd(
+                _lib.ptr(axis), _lib.ptr(lamb), _lib.ptr(weight), _lib.ptr(env_gt), _lib.ptr(seg), _lib.ptr(stats),
+                B, K, R, C, envH, envW, 1, float(offset), _lib.stream_ptr(dev)), 'irb_sg_reconst_fwd')
+        ctx.save_for_backward(axis, lamb, weight, env_gt, seg, stats)
+        ctx.cfg = (envH, envW, float(offset))
+        tot = stats.sum(dim=0)
+        coef = torch.clamp(stats[:, 0] / torch.clamp(stats[:, 1], min=1e-5), 0.001, 1000).float()
+        num, cnt = tot[2].float(), tot[3].float()
+        ctx.mark_non_differentiable(cnt, coef)
+        return num, cnt, coef
+
+    @staticmethod
+    def backward(ctx, g_num, g_cnt, g_coef):
+        axis, lamb, weight, env_gt, seg, stats = ctx.saved_tensors
+        envH, envW, offset = ctx.cfg
+        B, K, _, R, C = axis.shape
+        dev = axis.device
+        need = ctx.needs_input_grad
+        if not any(need[:3]):
+            return (None,) * 8
+        g = g_num.detach().to(torch.float32).contiguous()
+        outs = [torch.empty_like(t) if need[i] else None for i, t in enumerate((axis, lamb, weight))]
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().irb_sg_reconst_bwd(
+                _lib.ptr(axis), _lib.ptr(lamb), _lib.ptr(weight), _lib.ptr(env_gt), _lib.ptr(seg), _lib.ptr(stats),
+                _lib.ptr(g), *[_lib.ptr(o) for o in outs], B, K, R, C, envH, envW, 1, offset, _lib.stream_ptr(dev)),
+                'irb_sg_reconst_bwd')
+        return tuple(outs) + (None,) * 5
+
+
 class _RenderEnv(torch.autograd.Function):
     """models.py:466-520 on pooled maps and a materialised env-map."""
 
@@ -264,6 +305,33 @@ class output2env():
         if self.SGNum <= self.MAX_FUSED_LOBES:
             env._irb_sg = (axisOrig, lambOrig, weightOrig, self.envHeight, self.envWidth)
         return env, axisOrig, lamb, weight
+
+    def reconstLoss(self, axisOrig, lambOrig, weightOrig, envmapsBatch, segEnvBatch, offset=1.0):
+        """Scale-invariant log-L2 reconstruction error of the predicted SG lighting against ``envmapsBatch``
+        (the block wrapperBRDFLight.py:172-188: output2env -> LSregress on the masked env-maps -> log-L2 / pixelNum /
+        3 / envWidth / envHeight) in three streaming passes over the ground truth; the predicted env-map is evaluated
+        in registers and never written.  ``segEnvBatch`` is [B,1,R,C] or the reference's [B,1,R,C,1,1].
+
+        Returns (reconstErr, coef[B]); to look at the scaled prediction call ``output2env`` and multiply by coef.
+        No host synchronisation (the reference's ``pixelNum`` is a ``.item()``-style host value, here it stays on the
+        device).  Extension over the reference API.
+        """
+        self._check(axisOrig, lambOrig, weightOrig)
+        B, K, _, R, C = axisOrig.shape
+        _chk(envmapsBatch, 'envmapsBatch', 6)
+        if tuple(envmapsBatch.shape) != (B, 3, R, C, self.envHeight, self.envWidth):
+            raise ValueError('envmapsBatch must be %s (got %s)'
+                             % ((B, 3, R, C, self.envHeight, self.envWidth), tuple(envmapsBatch.shape)))
+        _chk(segEnvBatch, 'segEnvBatch')
+        if segEnvBatch.numel() != B * R * C:
+            raise ValueError('segEnvBatch must hold one value per pixel, [B,1,R,C] (got %s)' % (tuple(segEnvBatch.shape),))
+        if envmapsBatch.requires_grad or segEnvBatch.requires_grad:
+            raise ValueError('reconstLoss differentiates w.r.t. the SG parameters only')
+        seg = segEnvBatch.reshape(B, 1, R, C)
+        num, cnt, coef = _SgReconstLoss.apply(axisOrig, lambOrig, weightOrig, envmapsBatch, seg, self.envHeight,
+                                              self.envWidth, float(offset))
+        err = num / torch.clamp(cnt, min=1e-5) / 3.0 / self.envWidth / self.envHeight
+        return err, coef
 
 
 class renderingLayer():

@@ -426,3 +426,47 @@ def test_lsregress_fused(irb):
         ref = pred * coef.view([nb] + [1] * (len(shape) - 1))
         assert relerr(out.detach().cpu().numpy(), ref.cpu().numpy()) <= 2e-5
         assert relerr(origin.grad.cpu().numpy(), coef.view([nb] + [1] * (len(shape) - 1)).expand(shape).cpu().numpy()) <= 2e-5
+
+
+@pytest.mark.parametrize('K', [5, 12, 24])
+def test_reconst_loss_fused(irb, K):
+    """output2env.reconstLoss (irb_sg_reconst_fwd/bwd: env-map never materialised) against the fp64 oracle chain
+    output2env -> LSregress(masked) -> log-L2 (wrapperBRDFLight.py:172-188): value, per-sample scale, SG gradients.
+    Fractional segmentation weights (the avg-pooled mask of the wrapper) and an all-masked sample included."""
+    from oracle import render_oracle as ro
+    B, R, C = 3, 12, 20
+    z = ro.synth_inputs(B, 2 * R, 2 * C, R, C, K, seed=77 + K, dtype=torch.float64, hi=1.0)
+    g = torch.Generator().manual_seed(5)
+    axis, lamb, weight = [t.clone().requires_grad_(True) for t in z[3:6]]
+    env_gt = (torch.rand(B, 3, R, C, 8, 16, generator=g, dtype=torch.float64) * 3.0).float().double()
+    seg = (torch.rand(B, 1, R, C, generator=g, dtype=torch.float64) > 0.3).double()
+    seg[:, :, :, :3] *= 0.5          # fractional weights
+    seg[2] = 0                       # sample without valid pixels: coef clamps through the 1e-5 guard
+    env64, _, _, _ = ro.output2env(axis, lamb, weight)
+    err64, _, num64, cnt64 = ro.reconst_loss(env64, env_gt, seg.view(B, 1, R, C, 1, 1))
+    err64.backward()
+
+    dev = torch.device('cuda')
+    a, l, w = [t.detach().float().to(dev).requires_grad_(True) for t in (axis, lamb, weight)]
+    o2e = irb.output2env(K, isCuda=True)
+    err, coef = o2e.reconstLoss(a, l, w, env_gt.float().to(dev), seg.float().to(dev).view(B, 1, R, C, 1, 1))
+    err.backward()
+    assert abs(float(err.detach()) - float(err64.detach())) <= 2e-5 * abs(float(err64.detach()))
+    m = seg.view(B, 1, R, C, 1, 1)
+    pg = (env64.detach() * m * env_gt * m).reshape(B, -1).sum(1)
+    pp = ((env64.detach() * m) ** 2).reshape(B, -1).sum(1)
+    coef64 = torch.clamp(pg / torch.clamp(pp, min=1e-5), 0.001, 1000)
+    assert relerr(coef.cpu().numpy(), coef64.numpy()) <= 2e-5
+    for ours, ref, name in ((a, axis, 'axis'), (l, lamb, 'lamb'), (w, weight, 'weight')):
+        e = relerr(ours.grad.cpu().numpy(), ref.grad.numpy())
+        assert e <= 1e-4, (name, e)
+    # composed path on the device (sg_to_env + fused LSregress + torch log-L2) agrees as well
+    a2, l2, w2 = [t.detach().clone().requires_grad_(True) for t in (a, l, w)]
+    env, _, _, _ = o2e.output2env(a2, l2, w2)
+    mm = seg.float().to(dev).view(B, 1, R, C, 1, 1).expand_as(env)
+    gt = env_gt.float().to(dev)
+    scaled = irb.LSregress(env.detach() * mm, gt * mm, env)
+    err2 = (((torch.log(scaled + 1) - torch.log(gt + 1)) ** 2) * mm).sum() / max(float(seg.sum()), 1e-5) / 3 / 16 / 8
+    err2.backward()
+    assert abs(float(err2.detach()) - float(err.detach())) <= 2e-5 * abs(float(err.detach()))
+    assert relerr(a.grad.cpu().numpy(), a2.grad.cpu().numpy()) <= 1e-4
