@@ -125,10 +125,13 @@ int irb_lsregress(const float* pred, const float* gt, const float* origin, float
  *   num = sum((log(envScaled + off) - log(envGT + off))^2 * seg)               (wrapperBRDFLight.py:183-187)
  * without materialising envPred.  env_gt [B,3,R,C,envH,envW]; seg [B,1,R,C] (mask or fractional weight);
  * stats [B,4] fp64 out = {sum(E G s^2), sum(E^2 s^2), num_b, sum(s)}; coef_b = clamp(stats0/max(stats1,1e-5), 1e-3, 1e3).
+ * fwd: when any of g_axis / g_lamb / g_weight is non-null the second pass also writes d(sum_b num_b)/d(parameter)
+ * (unit upstream gradient; the caller scales these small tensors), so a training step needs two passes, not three.
  * bwd: g_num = device scalar dL/d(sum_b num_b); writes the gradients w.r.t. the ORIGINAL SG parameters (coef is a
  * graph constant as in models.py:13).  Needs K <= 24, R*C % 4 == 0, 16-byte aligned buffers (else IRB_E_UNSUPPORTED). */
 int irb_sg_reconst_fwd(const float* axis, const float* lamb, const float* weight, const float* env_gt, const float* seg,
-                       double* stats, int B, int K, int R, int C, int envH, int envW, int warp, float offset, void* stream);
+                       double* stats, float* g_axis, float* g_lamb, float* g_weight, int B, int K, int R, int C, int envH,
+                       int envW, int warp, float offset, void* stream);
 int irb_sg_reconst_bwd(const float* axis, const float* lamb, const float* weight, const float* env_gt, const float* seg,
                        const double* stats, const float* g_num, float* g_axis, float* g_lamb, float* g_weight, int B, int K,
                        int R, int C, int envH, int envW, int warp, float offset, void* stream);

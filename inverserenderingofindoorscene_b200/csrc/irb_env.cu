@@ -144,8 +144,8 @@ extern "C" int irb_sg_to_env_bwd(const float* axis, const float* lamb, const flo
 // its SG lobes inside the kernels and compared with the ground truth on the fly, so the only large stream is the
 // ground-truth env-map (read once per pass).  stats[b] = {sum E G s^2, sum E^2 s^2, sum dlog^2 s, sum s} in fp64.
 extern "C" int irb_sg_reconst_fwd(const float* axis, const float* lamb, const float* weight, const float* env_gt,
-                                  const float* seg, double* stats, int B, int K, int R, int C, int envH, int envW, int warp,
-                                  float offset, void* stream) {
+                                  const float* seg, double* stats, float* g_axis, float* g_lamb, float* g_weight, int B, int K,
+                                  int R, int C, int envH, int envW, int warp, float offset, void* stream) {
     IRB_REQUIRE(B > 0 && K > 0 && R > 0 && C > 0, "sg_reconst_fwd: non-positive shape");
     IRB_REQUIRE(axis && lamb && weight && env_gt && seg && stats, "sg_reconst_fwd: null pointer");
     IRB_REQUIRE(offset > 0.f, "sg_reconst_fwd: offset must be positive");
@@ -153,7 +153,9 @@ extern "C" int irb_sg_reconst_fwd(const float* axis, const float* lamb, const fl
     if (int rc = mk_tab(tab, envH, envW, B, "sg_reconst_fwd")) return rc;
     SgEnvArgs s{};
     s.axis = axis; s.lamb = lamb; s.weight = weight; s.env_gt = env_gt; s.seg = seg; s.stats = stats; s.offset = offset;
+    s.g_axis = g_axis; s.g_lamb = g_lamb; s.g_weight = g_weight;
     s.B = B; s.K = K; s.R = R; s.C = C; s.warp = warp;
+    const bool with_grads = g_axis || g_lamb || g_weight;   // second pass = loss + unit-gradient in one sweep
     if (!sg_group_ok(s, env_gt)) {
         set_error("sg_reconst_fwd: needs K <= 24, R*C %% 4 == 0 and 16-byte aligned planes");
         return IRB_E_UNSUPPORTED;
@@ -167,13 +169,16 @@ extern "C" int irb_sg_reconst_fwd(const float* axis, const float* lamb, const fl
     int rc;
     if (K <= 6) {
         rc = launch_sg_group(sg_env_group_kernel<2, 1>, s, tab, 128, st, "sg_reconst_fwd(stats)");
-        if (!rc) rc = launch_sg_group(sg_env_group_kernel<3, 1>, s, tab, 128, st, "sg_reconst_fwd(loss)");
+        if (!rc) rc = with_grads ? launch_sg_group(sg_env_group_kernel<5, 1>, s, tab, 128, st, "sg_reconst_fwd(loss+grad)")
+                                 : launch_sg_group(sg_env_group_kernel<3, 1>, s, tab, 128, st, "sg_reconst_fwd(loss)");
     } else if (K <= 12) {
         rc = launch_sg_group(sg_env_group_kernel<2, 2>, s, tab, 64, st, "sg_reconst_fwd(stats)");
-        if (!rc) rc = launch_sg_group(sg_env_group_kernel<3, 2>, s, tab, 64, st, "sg_reconst_fwd(loss)");
+        if (!rc) rc = with_grads ? launch_sg_group(sg_env_group_kernel<5, 2>, s, tab, 64, st, "sg_reconst_fwd(loss+grad)")
+                                 : launch_sg_group(sg_env_group_kernel<3, 2>, s, tab, 64, st, "sg_reconst_fwd(loss)");
     } else {
         rc = launch_sg_group(sg_env_group_kernel<2, 4>, s, tab, 32, st, "sg_reconst_fwd(stats)");
-        if (!rc) rc = launch_sg_group(sg_env_group_kernel<3, 4>, s, tab, 32, st, "sg_reconst_fwd(loss)");
+        if (!rc) rc = with_grads ? launch_sg_group(sg_env_group_kernel<5, 4>, s, tab, 32, st, "sg_reconst_fwd(loss+grad)")
+                                 : launch_sg_group(sg_env_group_kernel<3, 4>, s, tab, 32, st, "sg_reconst_fwd(loss)");
     }
     return rc;
 }

@@ -35,6 +35,7 @@ __device__ __forceinline__ void issue_sg_tile(float* stage, uint64_t* bar, const
 //   2: per-sample regression sums  sum(E G s^2), sum(E^2 s^2), sum(s)           (models.LSregress, models.py:7-21)
 //   3: numerator  sum((log(c E + off) - log(G + off))^2 s)                        (wrapperBRDFLight.py:183-187)
 //   4: its gradient w.r.t. the SG parameters (c is a graph constant, models.py:13)
+//   5: 3 and 4 in one pass with a unit upstream gradient (the caller scales the small SG gradients afterwards)
 __device__ __forceinline__ void sg_block_add(float v, double* dst) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -50,7 +51,7 @@ __device__ __forceinline__ float fast_log(float x) {   // natural log via lg2.ap
 }
 
 template <int MODE, int TPP>
-__global__ void __launch_bounds__(128, ((MODE == 1 || MODE == 4) ? 3 : 4)) sg_env_group_kernel(const SgEnvArgs s, const __grid_constant__ EnvTab tab,
+__global__ void __launch_bounds__(128, ((MODE == 1 || MODE >= 4) ? 3 : 4)) sg_env_group_kernel(const SgEnvArgs s, const __grid_constant__ EnvTab tab,
                                                               const unsigned total_tiles, const unsigned tiles_per_img) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[2];
@@ -176,13 +177,14 @@ __global__ void __launch_bounds__(128, ((MODE == 1 || MODE == 4) ? 3 : 4)) sg_en
                 S2[i] = N2[i] = mx2[i] = my2[i] = mz2[i] = pk(0.f, 0.f);
                 gW2[0][i] = gW2[1][i] = gW2[2][i] = pk(0.f, 0.f);
             }
-            const float* gsrc = (MODE == 4) ? s.env_gt : s.g_env;
+            const float* gsrc = (MODE >= 4) ? s.env_gt : s.g_env;
             const float* gp0 = gsrc + ((b * 3 + 0) * plane + pix) * D;
             const float* gp1 = gsrc + ((b * 3 + 1) * plane + pix) * D;
             const float* gp2 = gsrc + ((b * 3 + 2) * plane + pix) * D;
-            const float sg4 = (MODE == 4 && active) ? s.seg[b * plane + pix] : 0.f;
-            const float coef4 = (MODE == 4) ? reconst_coef(s.stats + b * 4) : 1.f;
-            const float gfac = (MODE == 4) ? 2.f * coef4 * sg4 * s.g_num[0] : 0.f;
+            const float sg4 = (MODE >= 4 && active) ? s.seg[b * plane + pix] : 0.f;
+            const float coef4 = (MODE >= 4) ? reconst_coef(s.stats + b * 4) : 1.f;
+            const float gfac = (MODE >= 4) ? 2.f * coef4 * sg4 * (MODE == 4 ? s.g_num[0] : 1.f) : 0.f;
+            float lacc = 0.f;
             F4 n0 = ld4(gp0), n1 = ld4(gp1), n2 = ld4(gp2);
             for (int d0 = 0; d0 < D; d0 += 4) {
                 const F4 g0 = n0, g1 = n1, g2 = n2;
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(128, ((MODE == 1 || MODE == 4) ? 3 : 4)) sg_en
                     const float wx = tab.lx[d0 + u], wy = tab.ly[d0 + u], wz = tab.lz[d0 + u];
                     pk2 arg[NP2], e[NP2];
                     lobe_exps_pk<kLPT>(Lp, pk(wx, wx), pk(wy, wy), pk(wz, wz), arg, e);
-                    if (MODE == 4) {   // dL/dE_cd = g * 2 c s (log(cE+off) - log(G+off)) / (cE+off)
+                    if (MODE >= 4) {   // dL/dE_cd = g * 2 c s (log(cE+off) - log(G+off)) / (cE+off)
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
                             pk2 acc = mul2(W2[c][0], e[0]);
@@ -205,7 +207,9 @@ __global__ void __launch_bounds__(128, ((MODE == 1 || MODE == 4) ? 3 : 4)) sg_en
                             for (int i = 1; i < NP2; ++i) acc = fma2(W2[c][i], e[i], acc);
                             const float Ecd = grp_allreduce<TPP>(hsum2(acc));
                             const float ce = coef4 * Ecd + s.offset;
-                            G[c][u] = gfac * (fast_log(ce) - fast_log(G[c][u] + s.offset)) * x_rcp(ce);
+                            const float dl = fast_log(ce) - fast_log(G[c][u] + s.offset);
+                            if (MODE == 5) lacc = fmaf(dl, dl, lacc);
+                            G[c][u] = gfac * dl * x_rcp(ce);
                         }
                     }
                     const pk2 G0 = pk(G[0][u], G[0][u]), G1 = pk(G[1][u], G[1][u]), G2 = pk(G[2][u], G[2][u]);
@@ -224,6 +228,8 @@ __global__ void __launch_bounds__(128, ((MODE == 1 || MODE == 4) ? 3 : 4)) sg_en
                     }
                 }
             }
+            // every lane of a group holds the same sum; lanes past the end of the plane worked on unstaged data
+            if (MODE == 5) sg_block_add((active && h == 0) ? lacc * sg4 : 0.f, s.stats + b * 4 + 2);
             if (active) {
 #pragma unroll
                 for (int i = 0; i < NP2; ++i) {

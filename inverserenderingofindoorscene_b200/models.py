@@ -137,12 +137,16 @@ class _SgReconstLoss(torch.autograd.Function):
         B, K, _, R, C = axis.shape
         dev = axis.device
         stats = torch.empty(B, 4, device=dev, dtype=torch.float64)
+        # the SG gradients are small (7K floats per pixel against the 384 of the env-map): when they are wanted the
+        # second pass computes them together with the loss for a unit upstream gradient, and backward only scales them
+        need = ctx.needs_input_grad
+        unit = [torch.empty_like(t) if need[i] else None for i, t in enumerate((axis, lamb, weight))]
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().irb_sg_reconst_fwd(
                 _lib.ptr(axis), _lib.ptr(lamb), _lib.ptr(weight), _lib.ptr(env_gt), _lib.ptr(seg), _lib.ptr(stats),
-                B, K, R, C, envH, envW, 1, float(offset), _lib.stream_ptr(dev)), 'irb_sg_reconst_fwd')
-        ctx.save_for_backward(axis, lamb, weight, env_gt, seg, stats)
-        ctx.cfg = (envH, envW, float(offset))
+                *[_lib.ptr(u) for u in unit], B, K, R, C, envH, envW, 1, float(offset), _lib.stream_ptr(dev)),
+                'irb_sg_reconst_fwd')
+        ctx.unit = unit
         tot = stats.sum(dim=0)
         coef = torch.clamp(stats[:, 0] / torch.clamp(stats[:, 1], min=1e-5), 0.001, 1000).float()
         num, cnt = tot[2].float(), tot[3].float()
@@ -151,21 +155,8 @@ class _SgReconstLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_num, g_cnt, g_coef):
-        axis, lamb, weight, env_gt, seg, stats = ctx.saved_tensors
-        envH, envW, offset = ctx.cfg
-        B, K, _, R, C = axis.shape
-        dev = axis.device
-        need = ctx.needs_input_grad
-        if not any(need[:3]):
-            return (None,) * 8
-        g = g_num.detach().to(torch.float32).contiguous()
-        outs = [torch.empty_like(t) if need[i] else None for i, t in enumerate((axis, lamb, weight))]
-        with torch.cuda.device(dev):
-            _lib.check(_lib.lib().irb_sg_reconst_bwd(
-                _lib.ptr(axis), _lib.ptr(lamb), _lib.ptr(weight), _lib.ptr(env_gt), _lib.ptr(seg), _lib.ptr(stats),
-                _lib.ptr(g), *[_lib.ptr(o) for o in outs], B, K, R, C, envH, envW, 1, offset, _lib.stream_ptr(dev)),
-                'irb_sg_reconst_bwd')
-        return tuple(outs) + (None,) * 5
+        g = g_num.detach().to(torch.float32)
+        return tuple(None if u is None else u * g for u in ctx.unit) + (None,) * 5
 
 
 class _RenderEnv(torch.autograd.Function):

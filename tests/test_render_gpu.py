@@ -470,3 +470,19 @@ def test_reconst_loss_fused(irb, K):
     err2.backward()
     assert abs(float(err2.detach()) - float(err.detach())) <= 2e-5 * abs(float(err.detach()))
     assert relerr(a.grad.cpu().numpy(), a2.grad.cpu().numpy()) <= 1e-4
+    # the separate-gradient entry point of the C ABI (three-pass form) gives the same gradients
+    from inverserenderingofindoorscene_b200 import _lib
+    a3, l3, w3 = [t.detach().contiguous() for t in (a, l, w)]
+    gtd, sgd = gt.contiguous(), seg.float().to(dev).contiguous()
+    stats = torch.empty(B, 4, device=dev, dtype=torch.float64)
+    st = _lib.stream_ptr(dev)
+    _lib.check(_lib.lib().irb_sg_reconst_fwd(_lib.ptr(a3), _lib.ptr(l3), _lib.ptr(w3), _lib.ptr(gtd), _lib.ptr(sgd),
+                                             _lib.ptr(stats), None, None, None, B, K, R, C, 8, 16, 1, 1.0, st), 'fwd')
+    gnum = torch.tensor([1.0 / max(float(seg.sum()), 1e-5) / 3 / 16 / 8], device=dev)
+    ga, gl, gw = torch.empty_like(a3), torch.empty_like(l3), torch.empty_like(w3)
+    _lib.check(_lib.lib().irb_sg_reconst_bwd(_lib.ptr(a3), _lib.ptr(l3), _lib.ptr(w3), _lib.ptr(gtd), _lib.ptr(sgd),
+                                             _lib.ptr(stats), _lib.ptr(gnum), _lib.ptr(ga), _lib.ptr(gl), _lib.ptr(gw),
+                                             B, K, R, C, 8, 16, 1, 1.0, st), 'bwd')
+    assert abs(float(stats[:, 2].sum()) * float(gnum) - float(err.detach())) <= 2e-5 * abs(float(err.detach()))
+    for ours, ref in ((ga, a.grad), (gl, l.grad), (gw, w.grad)):
+        assert relerr(ours.cpu().numpy(), ref.cpu().numpy()) <= 2e-5
