@@ -192,6 +192,49 @@ static int launch_tma(KernelT kernel, const RenderSgArgs& a, const EnvTab& tab, 
     return check_launch(what);
 }
 
+// lobe-split group kernels: same persistent launch, plus the tensor maps of the staged planes (IRB_TMA_TENSOR=0 keeps the
+// per-plane bulk copies for A/B runs)
+template <typename KernelT>
+static int launch_group(KernelT kernel, const RenderSgArgs& a, const EnvTab& tab, bool bwd, cudaStream_t st, const char* what,
+                        int tile) {
+    const size_t plane = (size_t)a.R * a.C;
+    const size_t tiles_per_img = (plane + tile - 1) / tile;
+    const size_t total = tiles_per_img * (size_t)a.B;
+    if (total >= 0xffffffffull || plane >= 0x7fffffffull) {
+        set_error("%s: too many tiles", what);
+        return IRB_E_UNSUPPORTED;
+    }
+    TileMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    const char* tt = getenv("IRB_TMA_TENSOR");
+    if (!(tt && tt[0] == '0')) {
+        const unsigned K = (unsigned)a.K, B = (unsigned)a.B, T = (unsigned)tile;
+        bool ok = make_tile_map(&maps.m[0], a.albedo, plane, 3, B, T) && make_tile_map(&maps.m[1], a.normal, plane, 3, B, T) &&
+                  make_tile_map(&maps.m[2], a.rough, plane, 1, B, T) && make_tile_map(&maps.m[3], a.view, plane, 3, 1, T) &&
+                  make_tile_map(&maps.m[4], a.axis, plane, 3 * K, B, T) && make_tile_map(&maps.m[5], a.lamb, plane, K, B, T) &&
+                  make_tile_map(&maps.m[6], a.weight, plane, 3 * K, B, T);
+        if (ok && bwd) ok = make_tile_map(&maps.m[7], a.g_diff, plane, 3, B, T) && make_tile_map(&maps.m[8], a.g_spec, plane, 3, B, T);
+        maps.on = ok ? 1 : 0;
+    }
+    const size_t smem = 2 * (size_t)stage_planes(a.K, bwd) * tile * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+        set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", what, smem, cudaGetErrorString(e));
+        return (int)e;
+    }
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem);
+    if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+    size_t grid = (size_t)device_sms() * per_sm;
+    if (grid > total) grid = total;
+    if (const char* cap = getenv("IRB_TMA_MAX_CTAS")) {
+        const long c = atol(cap);
+        if (c > 0 && (size_t)c < grid) grid = (size_t)c;
+    }
+    kernel<<<(unsigned)grid, kThreads, smem, st>>>(a, tab, maps, (unsigned)total, (unsigned)tiles_per_img);
+    return check_launch(what);
+}
+
 // Kernel variant.  Measured on B200 (profiles/r01, config 2): lobe-split "group" kernels 1.03 ms fwd / 2.26 ms bwd,
 // single-thread-per-pixel staged "tma1" 1.10 / 2.38 ms, plain (no staging) 1.23 / 3.41 ms -> group is the default.
 // IRB_RENDER_VARIANT = group | tma1 | plain overrides it (A/B runs and tests).
@@ -250,9 +293,9 @@ extern "C" int irb_render_sg_fwd(const float* albedo, const float* normal, const
     if (variant == 0) {
         int rc;
         const char* w = "render_sg_fwd(group)";
-        if (K <= 6) rc = launch_tma(render_sg_group_kernel<0, 1, false, false, 4>, a, tab, false, st, w, kThreads / 1);
-        else if (K <= 12) rc = launch_tma(render_sg_group_kernel<0, 2, false, false, 4>, a, tab, false, st, w, kThreads / 2);
-        else rc = launch_tma(render_sg_group_kernel<0, 4, false, false, 4>, a, tab, false, st, w, kThreads / 4);
+        if (K <= 6) rc = launch_group(render_sg_group_kernel<0, 1, false, false, 4>, a, tab, false, st, w, kThreads / 1);
+        else if (K <= 12) rc = launch_group(render_sg_group_kernel<0, 2, false, false, 4>, a, tab, false, st, w, kThreads / 2);
+        else rc = launch_group(render_sg_group_kernel<0, 4, false, false, 4>, a, tab, false, st, w, kThreads / 4);
         if (rc) return rc;
         a.only_irregular = 1;  // follow-up: the clamped / degenerate pixels, general world-space path
     }
@@ -298,11 +341,11 @@ extern "C" int irb_render_sg_bwd(const float* albedo, const float* normal, const
         const char* mb = getenv("IRB_BWD_MINB");  // A/B knob: resident CTAs the full backward is compiled for (2: 255 regs, 3: 168, 4: 128)
         const int minb = (mb && mb[0] >= '2' && mb[0] <= '4') ? mb[0] - '0' : 2;
 #define IRB_GROUP_BWD(TPP)                                                                                                   \
-    (pix && lobe ? (minb == 4   ? launch_tma(render_sg_group_kernel<1, TPP, true, true, 4>, a, tab, true, st, w, kThreads / TPP) \
-                    : minb == 3 ? launch_tma(render_sg_group_kernel<1, TPP, true, true, 3>, a, tab, true, st, w, kThreads / TPP) \
-                                : launch_tma(render_sg_group_kernel<1, TPP, true, true, 2>, a, tab, true, st, w, kThreads / TPP)) \
-     : pix      ? launch_tma(render_sg_group_kernel<1, TPP, true, false, 3>, a, tab, true, st, w, kThreads / TPP)            \
-                : launch_tma(render_sg_group_kernel<1, TPP, false, true, 3>, a, tab, true, st, w, kThreads / TPP))
+    (pix && lobe ? (minb == 4   ? launch_group(render_sg_group_kernel<1, TPP, true, true, 4>, a, tab, true, st, w, kThreads / TPP) \
+                    : minb == 3 ? launch_group(render_sg_group_kernel<1, TPP, true, true, 3>, a, tab, true, st, w, kThreads / TPP) \
+                                : launch_group(render_sg_group_kernel<1, TPP, true, true, 2>, a, tab, true, st, w, kThreads / TPP)) \
+     : pix      ? launch_group(render_sg_group_kernel<1, TPP, true, false, 3>, a, tab, true, st, w, kThreads / TPP)            \
+                : launch_group(render_sg_group_kernel<1, TPP, false, true, 3>, a, tab, true, st, w, kThreads / TPP))
         if (K <= 6) rc = IRB_GROUP_BWD(1);
         else if (K <= 12) rc = IRB_GROUP_BWD(2);
         else rc = IRB_GROUP_BWD(4);

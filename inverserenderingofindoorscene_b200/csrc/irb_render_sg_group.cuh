@@ -17,11 +17,32 @@
 
 namespace irb {
 
-__device__ __forceinline__ void issue_tile_n(float* stage, uint64_t* bar, const RenderSgArgs& a, size_t tile, size_t tiles_per_img,
-                                             bool bwd, int PT) {
+__device__ __forceinline__ void issue_tile_n(float* stage, uint64_t* bar, const RenderSgArgs& a, const TileMaps& maps, size_t tile,
+                                             size_t tiles_per_img, bool bwd, int PT) {
     const int lane = threadIdx.x & 31;
     const size_t plane = (size_t)a.R * a.C;
     const size_t b = tile / tiles_per_img, pix0 = (tile % tiles_per_img) * (size_t)PT;
+    if (maps.on) {
+        // one tiled copy per tensor (7 forward / 9 backward) instead of one bulk copy per plane (7K+10 / 7K+16): the
+        // per-plane form cost the producer warp ~75 cycles per copy, 11 % of its time, and the other warps waited for it
+        if (lane == 0) {
+            const int K = a.K;
+            mbar_expect_tx(bar, (uint32_t)stage_planes(K, bwd) * (uint32_t)PT * 4u);
+            const int c0 = (int)pix0, cb = (int)b;
+            tma_load_3d(stage, &maps.m[0], c0, 0, cb, bar);
+            tma_load_3d(stage + 3 * PT, &maps.m[1], c0, 0, cb, bar);
+            tma_load_3d(stage + 6 * PT, &maps.m[2], c0, 0, cb, bar);
+            tma_load_3d(stage + 7 * PT, &maps.m[3], c0, 0, 0, bar);
+            tma_load_3d(stage + 10 * PT, &maps.m[4], c0, 0, cb, bar);
+            tma_load_3d(stage + (10 + 3 * K) * PT, &maps.m[5], c0, 0, cb, bar);
+            tma_load_3d(stage + (10 + 4 * K) * PT, &maps.m[6], c0, 0, cb, bar);
+            if (bwd) {
+                tma_load_3d(stage + (10 + 7 * K) * PT, &maps.m[7], c0, 0, cb, bar);
+                tma_load_3d(stage + (13 + 7 * K) * PT, &maps.m[8], c0, 0, cb, bar);
+            }
+        }
+        return;
+    }
     const uint32_t valid = (uint32_t)((plane - pix0) < (size_t)PT ? (plane - pix0) : (size_t)PT);
     const uint32_t bytes = valid * 4u;
     const int K = a.K;
@@ -293,6 +314,7 @@ __device__ __forceinline__ void group_tile_bwd(const RenderSgArgs& a, const Rend
 // MODE 0 forward, 1 backward
 template <int MODE, int TPP, bool PIX, bool LOBE, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) render_sg_group_kernel(const RenderSgArgs a, const __grid_constant__ EnvTab tab,
+                                                                          const __grid_constant__ TileMaps maps,
                                                                           const unsigned total_tiles, const unsigned tiles_per_img) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2];
@@ -322,7 +344,7 @@ __global__ void __launch_bounds__(kThreads, MINB) render_sg_group_kernel(const R
     const size_t plane = (size_t)a.R * a.C;
     const int q = threadIdx.x / TPP, h = threadIdx.x % TPP;
     unsigned t = blockIdx.x;
-    if (t < total_tiles && threadIdx.x < 32) issue_tile_n(stage0, &full_bar[0], a, t, tiles_per_img, BWD, PT);
+    if (t < total_tiles && threadIdx.x < 32) issue_tile_n(stage0, &full_bar[0], a, maps, t, tiles_per_img, BWD, PT);
     for (unsigned it = 0; t < total_tiles; ++it, t += gridDim.x) {
         const int s = it & 1;
         float* const cur = s ? stage1 : stage0;
@@ -331,7 +353,7 @@ __global__ void __launch_bounds__(kThreads, MINB) render_sg_group_kernel(const R
             const unsigned kfill = (it + 1) >> 1;            // fill index of stage s^1
             if (kfill >= 1) mbar_wait(&empty_bar[s ^ 1], (kfill - 1) & 1);   // everyone finished the previous tenant
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue_tile_n(s ? stage0 : stage1, &full_bar[s ^ 1], a, tn, tiles_per_img, BWD, PT);
+            issue_tile_n(s ? stage0 : stage1, &full_bar[s ^ 1], a, maps, tn, tiles_per_img, BWD, PT);
         }
         mbar_wait(&full_bar[s], (it >> 1) & 1);
         const size_t b = t / tiles_per_img, pix0 = (size_t)(t % tiles_per_img) * PT;

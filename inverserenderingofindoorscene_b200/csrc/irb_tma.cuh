@@ -2,7 +2,46 @@
 #pragma once
 #include <stdint.h>
 
+#include <cuda.h>   // CUtensorMap and its enums only; the encoder is fetched with cudaGetDriverEntryPoint (no -lcuda)
+
 namespace irb {
+
+// Tensor maps of the planes a tile stages, in stage order.  on = 0: descriptors unavailable, kernels fall back to one
+// cp.async.bulk per plane.
+constexpr int kMaxTileMaps = 9;
+struct TileMaps {
+    CUtensorMap m[kMaxTileMaps];
+    int on;
+};
+
+typedef CUresult (*irb_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline irb_encode_tiled_fn tile_map_encoder() {
+    static irb_encode_tiled_fn fn = []() -> irb_encode_tiled_fn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return (irb_encode_tiled_fn)p;
+    }();
+    return fn;
+}
+
+// fp32 tensor [nb, rows, plane] (contiguous), box = [1, rows, tile] -> false when it cannot be described
+inline bool make_tile_map(CUtensorMap* m, const float* base, size_t plane, unsigned rows, unsigned nb, unsigned tile) {
+    irb_encode_tiled_fn fn = tile_map_encoder();
+    if (!fn || plane < tile || rows == 0 || rows > 256 || tile > 256 || plane % 4 != 0 || ((uintptr_t)base & 15u)) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)plane, rows, nb};
+    const cuuint64_t strides[2] = {(cuuint64_t)plane * 4, (cuuint64_t)plane * 4 * rows};
+    const cuuint32_t box[3] = {tile, rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 // ---------------------------------------------------------------------------------------------
 // TMA / mbarrier primitives (PTX; SASS: UBLKCP, SYNCS)
@@ -21,6 +60,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+// tiled (tensor-map) form: one instruction moves a [rows x PT] box of a [B, rows, plane] tensor; elements past the end
+// of the plane are zero-filled and still counted in the transaction bytes (SASS: UTMALDG)
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
