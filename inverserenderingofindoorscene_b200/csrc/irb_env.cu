@@ -8,6 +8,7 @@
 // irb_render_sg.cu is the fast path when the env-map comes from SG lobes.
 #include "irb_common.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 #include "irb_driver_env.cuh"
 #include "irb_tma.cuh"
@@ -64,7 +65,15 @@ static int launch_sg_group(KernelT kernel, const SgEnvArgs& s, const EnvTab& tab
         const long c = atol(cap);
         if (c > 0 && (size_t)c < grid) grid = (size_t)c;
     }
-    kernel<<<(unsigned)grid, 128, smem, st>>>(s, tab, (unsigned)total, (unsigned)tiles_per_img);
+    TileMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    const char* tt = getenv("IRB_TMA_TENSOR");
+    if (!(tt && tt[0] == '0') && plane < 0x7fffffffull) {
+        const unsigned K = (unsigned)s.K, B = (unsigned)s.B, T = (unsigned)tile;
+        maps.on = make_tile_map(&maps.m[0], s.axis, plane, 3 * K, B, T) && make_tile_map(&maps.m[1], s.lamb, plane, K, B, T) &&
+                  make_tile_map(&maps.m[2], s.weight, plane, 3 * K, B, T);
+    }
+    kernel<<<(unsigned)grid, 128, smem, st>>>(s, tab, maps, (unsigned)total, (unsigned)tiles_per_img);
     return check_launch(what);
 }
 

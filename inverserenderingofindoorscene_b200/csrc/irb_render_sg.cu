@@ -20,6 +20,7 @@
 // loads, used when a plane is not 16-byte addressable (R*C % 4 != 0 or misaligned base pointers).
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "irb_common.cuh"
 #include "irb_driver.cuh"

@@ -11,11 +11,21 @@
 
 namespace irb {
 
-__device__ __forceinline__ void issue_sg_tile(float* stage, uint64_t* bar, const SgEnvArgs& s, size_t tile, size_t tiles_per_img,
-                                              int PT) {
+__device__ __forceinline__ void issue_sg_tile(float* stage, uint64_t* bar, const SgEnvArgs& s, const TileMaps& maps, size_t tile,
+                                              size_t tiles_per_img, int PT) {
     const int lane = threadIdx.x & 31;
     const size_t plane = (size_t)s.R * s.C;
     const size_t b = tile / tiles_per_img, pix0 = (tile % tiles_per_img) * (size_t)PT;
+    if (maps.on) {   // one tiled copy per tensor (irb_render_sg_group.cuh)
+        if (lane == 0) {
+            const int K = s.K;
+            mbar_expect_tx(bar, (uint32_t)(7 * K) * (uint32_t)PT * 4u);
+            tma_load_3d(stage, &maps.m[0], (int)pix0, 0, (int)b, bar);
+            tma_load_3d(stage + 3 * K * PT, &maps.m[1], (int)pix0, 0, (int)b, bar);
+            tma_load_3d(stage + 4 * K * PT, &maps.m[2], (int)pix0, 0, (int)b, bar);
+        }
+        return;
+    }
     const uint32_t valid = (uint32_t)((plane - pix0) < (size_t)PT ? (plane - pix0) : (size_t)PT);
     const uint32_t bytes = valid * 4u;
     const int K = s.K, np = 7 * K;
@@ -52,6 +62,7 @@ __device__ __forceinline__ float fast_log(float x) {   // natural log via lg2.ap
 
 template <int MODE, int TPP>
 __global__ void __launch_bounds__(128, ((MODE == 1 || MODE >= 4) ? 3 : 4)) sg_env_group_kernel(const SgEnvArgs s, const __grid_constant__ EnvTab tab,
+                                                              const __grid_constant__ TileMaps maps,
                                                               const unsigned total_tiles, const unsigned tiles_per_img) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[2];
@@ -69,14 +80,14 @@ __global__ void __launch_bounds__(128, ((MODE == 1 || MODE >= 4) ? 3 : 4)) sg_en
     const size_t plane = (size_t)s.R * s.C;
     const int q = threadIdx.x / TPP, h = threadIdx.x % TPP;
     unsigned t = blockIdx.x;
-    if (t < total_tiles && threadIdx.x < 32) issue_sg_tile(stage0, &full_bar[0], s, t, tiles_per_img, PT);
+    if (t < total_tiles && threadIdx.x < 32) issue_sg_tile(stage0, &full_bar[0], s, maps, t, tiles_per_img, PT);
     for (unsigned it = 0; t < total_tiles; ++it, t += gridDim.x) {
         const int sidx = it & 1;
         float* const cur = sidx ? stage1 : stage0;
         const unsigned tn = t + gridDim.x;
         if (tn < total_tiles && threadIdx.x < 32) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue_sg_tile(sidx ? stage0 : stage1, &full_bar[sidx ^ 1], s, tn, tiles_per_img, PT);
+            issue_sg_tile(sidx ? stage0 : stage1, &full_bar[sidx ^ 1], s, maps, tn, tiles_per_img, PT);
         }
         mbar_wait(&full_bar[sidx], (it >> 1) & 1);
         const size_t b = t / tiles_per_img, pix0 = (size_t)(t % tiles_per_img) * PT;
