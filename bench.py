@@ -398,7 +398,7 @@ def run_ours(args):
         flop_bwd = 128 * 250 * 2.0 * npx
         fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6
         # DRAM traffic of the backward kernel from the committed ncu --set full capture of this config
-        # (profiles/r01/ncu_prof_tma1_bwd_summary.txt: dram read 481.4 MB + write 397.0 MB per launch)
+        # (profiles/r01/ncu_v8_bwd_summary.txt: dram read 481.1 MB + write 408.5 MB per launch)
         traffic_bwd = 481.134592e6 + 408.537856e6 if (B, H, W, K) == (16, 240, 320, 12) else None
         line = {
             'metric': 'Mpixels/s render-layer fwd+bwd (240x320, 12 SG)', 'value': value, 'unit': 'Mpix/s',
