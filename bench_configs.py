@@ -117,6 +117,48 @@ def run_trainlight(models, dev, iters):
                     'output2env.reconstLoss + forwardSG (the env-map is never written)'}
 
 
+def run_trainlight_ddp(models, dev, iters):
+    """config 3 at N ranks (launch under torch.distributed.run): every rank holds 16 images (weak scaling), runs the
+    env-free loss block and normalises both losses by the batch-GLOBAL pixel counts through ONE 4-float all-reduce
+    (sharding.sharded_losses, NCCL).  Device-timed, max over ranks, printed by rank 0."""
+    import torch.distributed as dist
+    from inverserenderingofindoorscene_b200 import sharding
+    rank, world = dist.get_rank(), dist.get_world_size()
+    B, H, W, R, C, K = 16, 240, 320, 120, 160, 12
+    alb, n, rg, ax, lam, wt = rand_inputs(B, H, W, R, C, K, dev, 1236 + rank)
+    rl = models.renderingLayer(imWidth=C, imHeight=R, isCuda=True)
+    o2e = models.output2env(K, isCuda=True)
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    im = torch.rand(B, 3, R, C, device=dev, generator=g)
+    envgt = torch.rand(B, 3, R, C, 8, 16, device=dev, generator=g)
+    seg = (torch.rand(B, 1, R, C, device=dev, generator=g) > 0.2).float()
+
+    def step():
+        a, l, w = [t.detach().requires_grad_(True) for t in (ax, lam, wt)]
+        rec_num, rec_cnt, _ = o2e.reconstTerms(a, l, w, envgt, seg)
+        d, s = rl.forwardSG(alb, n, rg, a, l, w)
+        dS, sS = models.LSregressDiffSpec(d.detach(), s.detach(), im, d, s)
+        rend = torch.clamp(dS + sS, 0, 1)
+        r_num = ((rend - im) * (rend - im) * seg.expand_as(im)).sum()
+        rerr, rec = sharding.sharded_losses(r_num, seg.sum(), rec_num, rec_cnt)
+        (rerr + 10 * rec).backward()
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    return {'config': 'config 3: trainLight render-loss step (env-free), 16 images per GPU, loss all-reduce over NCCL',
+            'n_gpus': world, 'step_ms_max_over_ranks': ms, 'images_per_s': world * B / ms * 1e3, 'scaling': 'weak'}
+
+
 def run_unfused(models, dev, iters):
     B, R, C, K = 4, 240, 320, 12
     alb, n, rg, ax, lam, wt = rand_inputs(B, R, C, R, C, K, dev, 1237)
@@ -234,10 +276,28 @@ def main():
     from inverserenderingofindoorscene_b200 import BilateralLayer as BL
     from inverserenderingofindoorscene_b200 import _lib, models
     _lib.lib()
-    dev = torch.device('cuda', 0)
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    if world > 1 or 'trainlight_ddp' in args.which:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('MASTER_PORT', '29533')
+        os.environ.setdefault('RANK', '0')
+        os.environ.setdefault('WORLD_SIZE', '1')
+        dist.init_process_group('nccl', device_id=dev)
+        if world > 1:   # only the sharded config makes sense on several ranks
+            r = run_trainlight_ddp(models, dev, args.iters)
+            if dist.get_rank() == 0:
+                print(json.dumps(r))
+            dist.destroy_process_group()
+            return
     for w in args.which.split(','):
         if w == 'trainlight':
             r = run_trainlight(models, dev, args.iters)
+        elif w == 'trainlight_ddp':
+            r = run_trainlight_ddp(models, dev, args.iters)
         elif w == 'unfused':
             r = run_unfused(models, dev, args.iters)
         elif w == 'bilateral':
@@ -250,6 +310,8 @@ def main():
             continue
         print(json.dumps(r))
         sys.stdout.flush()
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == '__main__':

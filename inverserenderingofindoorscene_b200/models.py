@@ -300,13 +300,20 @@ class output2env():
     def reconstLoss(self, axisOrig, lambOrig, weightOrig, envmapsBatch, segEnvBatch, offset=1.0):
         """Scale-invariant log-L2 reconstruction error of the predicted SG lighting against ``envmapsBatch``
         (the block wrapperBRDFLight.py:172-188: output2env -> LSregress on the masked env-maps -> log-L2 / pixelNum /
-        3 / envWidth / envHeight) in three streaming passes over the ground truth; the predicted env-map is evaluated
+        3 / envWidth / envHeight) in two streaming passes over the ground truth; the predicted env-map is evaluated
         in registers and never written.  ``segEnvBatch`` is [B,1,R,C] or the reference's [B,1,R,C,1,1].
 
         Returns (reconstErr, coef[B]); to look at the scaled prediction call ``output2env`` and multiply by coef.
         No host synchronisation (the reference's ``pixelNum`` is a ``.item()``-style host value, here it stays on the
         device).  Extension over the reference API.
         """
+        num, cnt, coef = self.reconstTerms(axisOrig, lambOrig, weightOrig, envmapsBatch, segEnvBatch, offset)
+        err = num / torch.clamp(cnt, min=1e-5) / 3.0 / self.envWidth / self.envHeight
+        return err, coef
+
+    def reconstTerms(self, axisOrig, lambOrig, weightOrig, envmapsBatch, segEnvBatch, offset=1.0):
+        """(numerator, sum(seg), coef[B]) of ``reconstLoss`` -- the un-normalised pair a multi-GPU caller feeds to
+        ``sharding.sharded_losses`` so that the loss is normalised by the batch-GLOBAL pixel count."""
         self._check(axisOrig, lambOrig, weightOrig)
         B, K, _, R, C = axisOrig.shape
         _chk(envmapsBatch, 'envmapsBatch', 6)
@@ -319,10 +326,8 @@ class output2env():
         if envmapsBatch.requires_grad or segEnvBatch.requires_grad:
             raise ValueError('reconstLoss differentiates w.r.t. the SG parameters only')
         seg = segEnvBatch.reshape(B, 1, R, C)
-        num, cnt, coef = _SgReconstLoss.apply(axisOrig, lambOrig, weightOrig, envmapsBatch, seg, self.envHeight,
-                                              self.envWidth, float(offset))
-        err = num / torch.clamp(cnt, min=1e-5) / 3.0 / self.envWidth / self.envHeight
-        return err, coef
+        return _SgReconstLoss.apply(axisOrig, lambOrig, weightOrig, envmapsBatch, seg, self.envHeight, self.envWidth,
+                                    float(offset))
 
 
 class renderingLayer():
