@@ -370,6 +370,26 @@ __device__ __forceinline__ void block_atomic_add(double v, double* dst) {
     if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(dst, v);
 }
 
+// several sums at once: warp shuffle, then shared memory across the block's warps, then ONE atomic per sum and block
+template <int N>
+__device__ __forceinline__ void block_atomic_add_n(double (&v)[N], double* const (&dst)[N]) {
+    __shared__ double part[8][N];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_down_sync(0xffffffffu, v[i], o);
+    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+        for (int i = 0; i < N; ++i) part[w][i] = v[i];
+    __syncthreads();
+    if (threadIdx.x < N) {
+        double t = 0.0;
+        for (int j = 0; j < nw; ++j) t += part[j][threadIdx.x];
+        if (t != 0.0 && dst[threadIdx.x]) atomicAdd(dst[threadIdx.x], t);
+    }
+}
+
 // splat (ordered segmented sums), system diagonal, flat initialisation (BilateralGrid.py:134-145 / 160-168)
 __global__ void bg_setup_kernel(void* ws, BgLayout L, SolveArgs a) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -458,24 +478,33 @@ __device__ __forceinline__ bool bg_done(void* ws, const BgLayout& L, int b, int 
 
 // iteration `it`, step 1:  p = z + (rho/rho_prev) p   (z = M r);  also np[v][c] = n_v p_v[c], interleaved over
 // channels so that the mat-vec's neighbour gathers fetch all channels of a vertex in ONE 32-byte sector
-__global__ void bg_p_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
+template <int CH>
+__global__ void __launch_bounds__(256) bg_p_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     const size_t P = L.P;
     if (t >= (size_t)at<int>(ws, L.hdr)[b]) return;
+    bool done[CH];
+    double beta[CH], rv[CH], pold[CH];
+    const double* pprev = at<double>(ws, (it & 1) ? L.p1 : L.p0);
+    double* pnext = at<double>(ws, (it & 1) ? L.p0 : L.p1);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {   // all loads of the thread are issued before the first use
+        done[c] = bg_done(ws, L, b, c, it, a.tol);
+        beta[c] = (it > 0 && !done[c]) ? scal_ptr(ws, L, b, c, it)[0] / scal_ptr(ws, L, b, c, it - 1)[0] : 0.0;
+        const size_t o = ((size_t)b * CH + c) * P + t;
+        rv[c] = done[c] ? 0.0 : at<double>(ws, L.r)[o];
+        pold[c] = (it > 0 && !done[c]) ? pprev[o] : 0.0;
+    }
     const double nv = at<double>(ws, L.n0)[(size_t)b * P + t];
     const double mi = at<double>(ws, L.minv)[(size_t)b * P + t];
     double out[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int c = 0; c < L.ch; ++c) {
-        if (bg_done(ws, L, b, c, it, a.tol)) continue;
-        const size_t o = ((size_t)b * L.ch + c) * P + t;
-        const double z = mi * at<double>(ws, L.r)[o];
-        double pv = z;
-        if (it > 0) {
-            const double beta = scal_ptr(ws, L, b, c, it)[0] / scal_ptr(ws, L, b, c, it - 1)[0];
-            pv = fma(beta, at<double>(ws, (it & 1) ? L.p1 : L.p0)[o], z);
-        }
-        at<double>(ws, (it & 1) ? L.p0 : L.p1)[o] = pv;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        if (done[c]) continue;
+        const double z = mi * rv[c];
+        const double pv = (it > 0) ? fma(beta[c], pold[c], z) : z;
+        pnext[((size_t)b * CH + c) * P + t] = pv;
         out[c] = nv * pv;
     }
     double4* np = at<double4>(ws, L.np) + (size_t)b * P + t;
@@ -513,45 +542,63 @@ __global__ void bg_q_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
         mv = at<double>(ws, L.m)[(size_t)b * P + t];
         wsp = at<double>(ws, L.wsplat)[(size_t)b * P + t];
     }
+    double pq[BG_MAX_CH] = {0.0, 0.0, 0.0, 0.0};
+    double* dst[BG_MAX_CH] = {nullptr, nullptr, nullptr, nullptr};
     for (int c = 0; c < L.ch; ++c) {
         if (bg_done(ws, L, b, c, it, a.tol)) continue;  // uniform per (image, channel)
-        double pq = 0.0;
+        dst[c] = scal_ptr(ws, L, b, c, it) + 1;
         if (ok) {
             const size_t o = ((size_t)b * L.ch + c) * P + t;
             const double pv = at<double>(ws, (it & 1) ? L.p0 : L.p1)[o];
             const double q = a.lam * (mv * pv - nv * bl[c]) + wsp * pv;
             at<double>(ws, L.q)[o] = q;
-            pq = pv * q;
+            pq[c] = pv * q;
         }
-        block_atomic_add(pq, scal_ptr(ws, L, b, c, it) + 1);
     }
+    block_atomic_add_n<BG_MAX_CH>(pq, dst);
 }
 
 // iteration `it`, second half: alpha = rho/pq ; x += alpha p ; r -= alpha q ; next rho, rr
-__global__ void bg_xr_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
+template <int CH>
+__global__ void __launch_bounds__(256) bg_xr_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     const size_t P = L.P;
     const int V = at<int>(ws, L.hdr)[b];
     const bool ok = t < (size_t)V;
-    for (int c = 0; c < L.ch; ++c) {
-        if (bg_done(ws, L, b, c, it, a.tol)) continue;
-        double rho = 0.0, rr = 0.0;
-        if (ok) {
-            const double* s = scal_ptr(ws, L, b, c, it);
-            const double alpha = s[0] / s[1];
-            const size_t o = ((size_t)b * L.ch + c) * P + t;
-            const double pv = at<double>(ws, (it & 1) ? L.p0 : L.p1)[o];
-            a.x[o] += alpha * pv;
-            const double r = at<double>(ws, L.r)[o] - alpha * at<double>(ws, L.q)[o];
-            at<double>(ws, L.r)[o] = r;
-            rho = r * at<double>(ws, L.minv)[(size_t)b * P + t] * r;
-            rr = r * r;
-        }
+    double sums[2 * CH];
+    double* dst[2 * CH];
+    double alpha[CH], pv[CH], xv[CH], rv[CH], qv[CH];
+    const double* pcur = at<double>(ws, (it & 1) ? L.p0 : L.p1);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {   // all loads first, then the arithmetic, then one reduction for the 2*CH sums
+        const bool done = bg_done(ws, L, b, c, it, a.tol);
+        const double* s = scal_ptr(ws, L, b, c, it);
         double* sn = scal_ptr(ws, L, b, c, it + 1);
-        block_atomic_add(rho, sn + 0);
-        block_atomic_add(rr, sn + 2);
+        dst[2 * c] = done ? nullptr : sn + 0;
+        dst[2 * c + 1] = done ? nullptr : sn + 2;
+        alpha[c] = done ? 0.0 : s[0] / s[1];
+        const size_t o = ((size_t)b * CH + c) * P + t;
+        const bool ld = ok && !done;
+        pv[c] = ld ? pcur[o] : 0.0;
+        xv[c] = ld ? a.x[o] : 0.0;
+        rv[c] = ld ? at<double>(ws, L.r)[o] : 0.0;
+        qv[c] = ld ? at<double>(ws, L.q)[o] : 0.0;
     }
+    const double mi = ok ? at<double>(ws, L.minv)[(size_t)b * P + t] : 0.0;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        sums[2 * c] = sums[2 * c + 1] = 0.0;
+        if (ok && dst[2 * c]) {
+            const size_t o = ((size_t)b * CH + c) * P + t;
+            a.x[o] = xv[c] + alpha[c] * pv[c];
+            const double r = rv[c] - alpha[c] * qv[c];
+            at<double>(ws, L.r)[o] = r;
+            sums[2 * c] = r * mi * r;
+            sums[2 * c + 1] = r * r;
+        }
+    }
+    block_atomic_add_n<2 * CH>(sums, dst);
 }
 
 // slice (BilateralGrid.py:93-94) -> fp32 output
@@ -589,9 +636,19 @@ static int run_pcg(void* ws, const BgLayout& L, SolveArgs a, int maxiter, cudaSt
     bg_setup_kernel<<<grid, 256, 0, st>>>(ws, L, a);
     bg_r0_kernel<<<grid, 256, 0, st>>>(ws, L, a);
     for (int it = 0; it < maxiter; ++it) {
-        bg_p_kernel<<<grid, 256, 0, st>>>(ws, L, a, it);
+        switch (L.ch) {
+            case 1: bg_p_kernel<1><<<grid, 256, 0, st>>>(ws, L, a, it); break;
+            case 2: bg_p_kernel<2><<<grid, 256, 0, st>>>(ws, L, a, it); break;
+            case 3: bg_p_kernel<3><<<grid, 256, 0, st>>>(ws, L, a, it); break;
+            default: bg_p_kernel<4><<<grid, 256, 0, st>>>(ws, L, a, it); break;
+        }
         bg_q_kernel<<<grid, 256, 0, st>>>(ws, L, a, it);
-        bg_xr_kernel<<<grid, 256, 0, st>>>(ws, L, a, it);
+        switch (L.ch) {
+            case 1: bg_xr_kernel<1><<<grid, 256, 0, st>>>(ws, L, a, it); break;
+            case 2: bg_xr_kernel<2><<<grid, 256, 0, st>>>(ws, L, a, it); break;
+            case 3: bg_xr_kernel<3><<<grid, 256, 0, st>>>(ws, L, a, it); break;
+            default: bg_xr_kernel<4><<<grid, 256, 0, st>>>(ws, L, a, it); break;
+        }
     }
     return check_launch("bilateral pcg");
 }
