@@ -25,7 +25,7 @@ constexpr int BG_MAX_CH = 4;
 struct BgLayout {
     int B, H, W, ch;
     size_t P;
-    size_t hdr, idx, vstart, ukeys, nbr, n0, n1, m, m0, keysA, keysB, payA, payB, hist;
+    size_t hdr, idx, vstart, ukeys, nbr, n0, n1, m, m0, keysA, keysB, payA, payB, hist, dtot;
     size_t wsplat, minv, bvec, r, p0, p1, q, sol, np, scal, total;
 };
 
@@ -52,6 +52,7 @@ static BgLayout make_layout(int B, int H, int W, int ch) {
     L.payA = take(4 * P * Bz);
     L.payB = take(4 * P * Bz);
     L.hist = take(4 * 256 * (size_t)256 * Bz);  // radix-sort bucket counters [img][digit][warp-chunk]
+    L.dtot = take(4 * 256 * (size_t)8 * Bz);    // per-digit totals of every pass [pass][img][digit]
     L.wsplat = take(8 * P * Bz);
     L.minv = take(8 * P * Bz);
     const size_t vc = 8 * P * Bz * (size_t)(ch > 0 ? ch : 1);
@@ -139,45 +140,45 @@ __global__ void __launch_bounds__(SORT_CTA_WARPS * 32) bg_sort_hist_kernel(void*
     for (size_t i = beg + lane; i < end; i += 32) atomicAdd(&sh[wl][(unsigned)(io.kin[i] >> shift) & 255u], 1u);
     __syncwarp();
     unsigned* hist = at<unsigned>(ws, L.hist) + (size_t)b * 256 * SORT_WPI;
-    for (int d = lane; d < 256; d += 32) hist[(size_t)d * SORT_WPI + warp] = sh[wl][d];
+    unsigned* dtot = at<unsigned>(ws, L.dtot) + ((size_t)pass * L.B + b) * 256;
+    for (int d = lane; d < 256; d += 32) {
+        const unsigned c = sh[wl][d];
+        hist[(size_t)d * SORT_WPI + warp] = c;
+        if (c) atomicAdd(&dtot[d], c);
+    }
 }
 
-__global__ void __launch_bounds__(1024) bg_sort_scan_kernel(void* ws, BgLayout L) {
-    __shared__ unsigned wtot[32];
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned* hist = at<unsigned>(ws, L.hist) + (size_t)b * 256 * SORT_WPI;
-    constexpr int PER = 256 * SORT_WPI / 1024;  // consecutive entries per thread
-    unsigned loc[PER], s = 0;
+// exclusive scan of the counters in (digit, chunk) order.  One warp per digit: its base is the sum of the totals of the
+// smaller digits (dtot, accumulated by the histogram kernel), its 256 chunk counters are 8 consecutive entries per lane.
+__global__ void __launch_bounds__(256) bg_sort_scan_kernel(void* ws, BgLayout L, int pass) {
+    static_assert(SORT_WPI == 256, "one lane owns 8 consecutive chunk counters");
+    const int b = blockIdx.y, lane = threadIdx.x & 31, d = blockIdx.x * 8 + (threadIdx.x >> 5);
+    unsigned* hist = at<unsigned>(ws, L.hist) + ((size_t)b * 256 + d) * SORT_WPI;
+    const unsigned* dtot = at<unsigned>(ws, L.dtot) + ((size_t)pass * L.B + b) * 256;
+    unsigned base = 0;
 #pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        loc[j] = hist[(size_t)tid * PER + j];
-        s += loc[j];
-    }
+    for (int j = 0; j < 8; ++j) base += (lane * 8 + j < d) ? dtot[lane * 8 + j] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) base += __shfl_xor_sync(0xffffffffu, base, o);
+    const uint4 lo = reinterpret_cast<const uint4*>(hist)[lane * 2], hi = reinterpret_cast<const uint4*>(hist)[lane * 2 + 1];
+    const unsigned loc[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    unsigned s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += loc[j];
     unsigned inc = s;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += v;
     }
-    if (lane == 31) wtot[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        const unsigned v = wtot[lane];
-        unsigned iv = v;
+    unsigned run = base + inc - s, out[8];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned u = __shfl_up_sync(0xffffffffu, iv, o);
-            if (lane >= o) iv += u;
-        }
-        wtot[lane] = iv - v;
-    }
-    __syncthreads();
-    unsigned run = wtot[warp] + inc - s;
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        hist[(size_t)tid * PER + j] = run;
+    for (int j = 0; j < 8; ++j) {
+        out[j] = run;
         run += loc[j];
     }
+    reinterpret_cast<uint4*>(hist)[lane * 2] = make_uint4(out[0], out[1], out[2], out[3]);
+    reinterpret_cast<uint4*>(hist)[lane * 2 + 1] = make_uint4(out[4], out[5], out[6], out[7]);
 }
 
 __global__ void __launch_bounds__(SORT_CTA_WARPS * 32) bg_sort_scatter_kernel(void* ws, BgLayout L, int pass) {
@@ -689,11 +690,12 @@ extern "C" int irb_bg_build(const float* guide, float guide_scale, int B, int H,
     // sort all 64 bits so that aliasing hashes are still ordered exactly like np.unique orders them
     const double maxc = fmax(fmax((double)W / sigma_spatial, (double)H / sigma_spatial), fmax(256.0 / sigma_luma, 384.0 / sigma_chroma));
     const int npass = maxc < 254.0 ? 5 : 7;  // odd: the sorted result must land in keysB / payB
+    cudaMemsetAsync(at<unsigned>(ws, L.dtot), 0, 4 * 256 * (size_t)8 * B, st);
     {
         const dim3 sgrid(SORT_WPI / SORT_CTA_WARPS, (unsigned)B);
         for (int pass = 0; pass < npass; ++pass) {
             bg_sort_hist_kernel<<<sgrid, SORT_CTA_WARPS * 32, 0, st>>>(ws, L, pass);
-            bg_sort_scan_kernel<<<B, 1024, 0, st>>>(ws, L);
+            bg_sort_scan_kernel<<<dim3(32, (unsigned)B), 256, 0, st>>>(ws, L, pass);
             bg_sort_scatter_kernel<<<sgrid, SORT_CTA_WARPS * 32, 0, st>>>(ws, L, pass);
         }
         bg_unique_count_kernel<<<sgrid, SORT_CTA_WARPS * 32, 0, st>>>(ws, L);
