@@ -136,6 +136,12 @@ int irb_sg_reconst_bwd(const float* axis, const float* lamb, const float* weight
                        const double* stats, const float* g_num, float* g_axis, float* g_lamb, float* g_weight, int B, int K,
                        int R, int C, int envH, int envW, int warp, float offset, void* stream);
 
+/* SG lighting -> diffuse irradiance ("shading") image: replaces utils.predToShading (utils.py:156-195, called from
+ * testReal.py:638).  pred [B,7K,R,C] = cat(axis[K,3], lambOrig[K], weightOrig[K,3]) per image (the reference passes
+ * B = 1); out [B,3,R,C] = max(sum_d cosEl_d sinEl_d * env_d, 0) over an envH x envW hemisphere table (16 x 32 in the
+ * reference; envH*envW <= 2048).  Forward only. */
+int irb_sg_shading(const float* pred, float* out, int B, int K, int R, int C, int envH, int envW, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Bilateral-grid solver.  Replaces BilateralGrid.BilateralGrid / bistochastize /
  * BilateralSolver.solve / solveGrad (BilateralGrid.py:44-207) and the per-image bridge

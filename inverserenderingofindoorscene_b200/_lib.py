@@ -29,6 +29,7 @@ SIGNATURES = {
     'irb_lsregress': [_P, _P, _P, _P, _P, _P, _I, C.c_longlong, _P],
     'irb_sg_reconst_fwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     'irb_sg_reconst_bwd': [_P] * 10 + [_I, _I, _I, _I, _I, _I, _I, _F, _P],
+    'irb_sg_shading': [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     'irb_bg_workspace_bytes': [_I, _I, _I, _I],
     'irb_bg_build': [_P, _F, _I, _I, _I, _D, _D, _D, _P, C.c_size_t, C.POINTER(C.c_int), _P],
     'irb_bg_vertex_index': [_P, _P, _I, _I, _I, _P],

@@ -4,20 +4,24 @@
     from inverserenderingofindoorscene_b200 import compat
     compat.patch_reference(models, BilateralLayer)
 
+(optionally ``compat.patch_reference(models, BilateralLayer, utils)`` to also route ``utils.predToShading``.)
+
 After this, ``models.renderingLayer``, ``models.output2env``, ``models.LSregress``,
 ``models.LSregressDiffSpec``, ``BilateralLayer.BilateralFunction`` and ``BilateralLayer.BilateralLayer``
 are the implementations of this package; the CNN classes stay the reference's.  ``unpatch`` restores.
 """
 from . import BilateralLayer as _bl
 from . import models as _models
+from . import utils as _utils
 
 _RENDER = ('renderingLayer', 'output2env', 'LSregress', 'LSregressDiffSpec')
 _BILAT = ('BilateralFunction', 'BilateralLayer')
+_UTILS = ('predToShading',)
 _saved = {}
 
 
-def patch_reference(ref_models=None, ref_bilateral_layer=None):
-    for mod, names, src in ((ref_models, _RENDER, _models), (ref_bilateral_layer, _BILAT, _bl)):
+def patch_reference(ref_models=None, ref_bilateral_layer=None, ref_utils=None):
+    for mod, names, src in ((ref_models, _RENDER, _models), (ref_bilateral_layer, _BILAT, _bl), (ref_utils, _UTILS, _utils)):
         if mod is None:
             continue
         for n in names:

@@ -123,9 +123,27 @@ def make_bilateral(ref_bg, name, H, W, ch, sig, bsp, seed, blur_sigma, B=1):
     print('wrote', path, os.path.getsize(path) // 1024, 'KiB')
 
 
+def make_shading(name, R, C, K, seed, hi=1.0):
+    """utils.predToShading (utils.py:156-195) on a seeded SG volume.  ``utils`` imports h5py (absent here, never used
+    on this path): an empty stub module stands in for it."""
+    sys.path.insert(0, REF)
+    sys.modules.setdefault('h5py', types.ModuleType('h5py'))
+    import utils as ref_utils  # noqa
+    _, _, _, axis, lamb, weight = ro.synth_inputs(1, R, C, R, C, K, seed=seed, dtype=torch.float32, hi=hi)
+    pred = torch.cat([axis.reshape(1, 3 * K, R, C), lamb, weight], dim=1).numpy().astype(np.float32)
+    shading = ref_utils.predToShading(pred, SGNum=K)
+    np.savez_compressed(os.path.join(GOLD, 'shading_%s.npz' % name), pred=pred, shading=shading,
+                        meta=np.array([R, C, K, 32, 16]))
+    print('shading_%s' % name, shading.shape, shading.dtype, float(shading.max()))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
+    if '--only-shading' in sys.argv:   # later addition: does not touch the committed render / bilateral fixtures
+        make_shading('k12', R=6, C=8, K=12, seed=1243, hi=0.9)
+        make_shading('k24_full', R=5, C=7, K=24, seed=1244, hi=1.0)
+        return
     ref, ref_bg = load_reference()
     # render: 2x pooling (trainLight geometry), full-domain and typical SG ranges
     make_render(ref, 'pool2_full', B=2, H=12, W=16, R=6, C=8, K=12, seed=1235, hi=1.0)
@@ -139,6 +157,8 @@ def main():
     make_bilateral(ref_bg, 'mode2', 40, 56, 1, (8, 2, 8), (300, 1e-5, 1e-5, 10), seed=1240, blur_sigma=3.0)
     make_bilateral(ref_bg, 'mode4', 40, 56, 1, (4, 2, 4), (100, 1e-5, 1e-5, 10), seed=1241, blur_sigma=2.0)
     make_bilateral(ref_bg, 'noise', 24, 32, 3, (8, 2, 7), (200, 1e-5, 1e-5, 12), seed=1242, blur_sigma=0.0)
+    make_shading('k12', R=6, C=8, K=12, seed=1243, hi=0.9)
+    make_shading('k24_full', R=5, C=7, K=24, seed=1244, hi=1.0)
 
 
 if __name__ == '__main__':

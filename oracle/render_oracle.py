@@ -249,6 +249,30 @@ def reconst_loss(envPred, envGT, segEnv, offset=1.0, envHeight=8, envWidth=16):
     return num / pixelNum / 3.0 / envWidth / envHeight, scaled, num, pixelNum
 
 
+def pred_to_shading(pred, envWidth=32, envHeight=16, SGNum=12, exact_warp=False):
+    """utils.py:156-195: pred [1,7K,R,C] (NumPy) -> shading [3,R,C] in fp64, direction by direction.
+    shading_c = max(sum_d cosEl_d sinEl_d sum_k tan(pi/2 .999 w_kc) exp(tan(pi/2 .999 lam_k)(a_k.w_d - 1)), 0)."""
+    import numpy as np
+    pred = np.asarray(pred)
+    K = SGNum
+    R, C = pred.shape[2], pred.shape[3]
+    p = pred[0].astype(np.float64) if exact_warp else pred[0]   # exact_warp: the fp64 truth the parity protocol measures against
+    axis = p[0:3 * K].reshape(K, 3, R, C).astype(np.float64)
+    # the tan warp runs in pred's own dtype (float32 array x Python scalar stays float32, utils.py:178-186); everything
+    # after it is promoted to float64 by the float64 direction table
+    lamb = np.tan(np.pi / 2.0 * (p[3 * K:4 * K].reshape(K, 1, R, C) * 0.999)).astype(np.float64)
+    weight = np.tan(np.pi / 2.0 * (p[4 * K:7 * K].reshape(K, 3, R, C) * 0.999)).astype(np.float64)
+    out = np.zeros((3, R, C), dtype=np.float64)
+    for i in range(envHeight):
+        el = (i + 0.5) / envHeight * np.pi / 2.0
+        for j in range(envWidth):
+            az = ((j + 0.5) / envWidth - 0.5) * 2 * np.pi
+            w = np.array([np.sin(el) * np.cos(az), np.sin(el) * np.sin(az), np.cos(el)])
+            dot = (axis * w.reshape(1, 3, 1, 1)).sum(axis=1, keepdims=True)          # [K,1,R,C]
+            out += (weight * np.exp(lamb * (dot - 1))).sum(axis=0) * (np.cos(el) * np.sin(el))
+    return np.maximum(out, 0.0)
+
+
 # --------------------------------------------------------------------------------------
 # seeded synthetic inputs (SURVEY.md 8d)
 # --------------------------------------------------------------------------------------
