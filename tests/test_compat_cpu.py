@@ -18,6 +18,30 @@ def test_patch_and_unpatch():
     assert ref_m.renderingLayer is sentinel
 
 
+def test_patch_utils():
+    from inverserenderingofindoorscene_b200 import utils
+    ref_u = types.ModuleType('utils')
+    keep = object()
+    ref_u.predToShading = keep
+    ref_u.writeEnvToFile = keep
+    compat.patch_reference(None, None, ref_u)
+    assert ref_u.predToShading is utils.predToShading and ref_u.writeEnvToFile is keep
+    compat.unpatch()
+    assert ref_u.predToShading is keep
+
+
+def test_pred_to_shading_refuses_cpu():
+    import numpy as np
+    import pytest
+    import torch
+    from inverserenderingofindoorscene_b200 import utils
+    with pytest.raises(ValueError):
+        utils.predToShading(torch.zeros(1, 84, 4, 4))          # CPU tensor
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            utils.predToShading(np.zeros((1, 84, 4, 4), np.float32))
+
+
 def test_bilateral_layer_shell_cpu():
     import torch
     layer = BilateralLayer.BilateralLayer(mode=2, isCuda=False)
