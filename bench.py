@@ -147,9 +147,18 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     threads, per_row = _best_threads(cores)
-    # size the per-step sample so that (steps+warmup) steps end within ~3 minutes
-    rows = int(max(48, min(H, 180.0 / max(1, args.steps + args.warmup) / max(per_row, 1e-6))))
+    # size the per-step sample so that the (steps+warmup) steps end within ~90 s: first guess from the thread probe,
+    # then one calibration step at that size (the probe's small samples under-estimate the per-row cost by ~2x)
+    nstep = max(1, args.steps + args.warmup)
+    rows = int(max(8, min(H, 90.0 / nstep / max(per_row, 1e-6))))
     step = cpu_step_fn(rows)
+    t0 = time.perf_counter()
+    step()
+    per_row = (time.perf_counter() - t0) / rows
+    rows2 = int(max(8, min(H, 90.0 / nstep / max(per_row, 1e-6))))
+    if rows2 != rows:
+        rows = rows2
+        step = cpu_step_fn(rows)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -424,7 +433,7 @@ def run_ours(args):
                                   'fwd_frac': flop_fwd / (fwd_ms * 1e-3) / fp32_peak}},
             'e2e': {'value': world * npx / (e2e_ms * 1e-3) / 1e6, 'unit': 'Mpix/s', 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': n_e2e},
-            'gpu_launches': 4 * args.steps,   # fwd and bwd: lobe-split kernel + irregular-pixel follow-up each
+            'gpu_launches': 2 * args.steps,   # one lobe-split kernel for the forward, one for the backward
             'clocks': clk,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -89,8 +89,30 @@ struct PixView {
     size_t b, pix, plane;
 };
 
+// Who works on a pixel.  Solo: one thread owns it (plain kernels, host check).  A warp-cooperative policy
+// (irb_render_sg_group.cuh) gives every lane a slice of the directions, sums the partial results across the warp and
+// lets one lane store.
+struct Solo {
+    IRB_HD static DirSlice slice() { return DirSlice{0, 1}; }
+    template <typename T> IRB_HD static void reduce(T&) {}
+    IRB_HD static bool leader() { return true; }
+};
+template <typename C, typename T> IRB_HD void coop_reduce(PixelGrad<T>& g) {
+    C::reduce(g.g_cx.x); C::reduce(g.g_cx.y); C::reduce(g.g_cx.z);
+    C::reduce(g.g_cy.x); C::reduce(g.g_cy.y); C::reduce(g.g_cy.z);
+    C::reduce(g.g_n.x); C::reduce(g.g_n.y); C::reduce(g.g_n.z);
+    C::reduce(g.G_n1); C::reduce(g.g_alpha2); C::reduce(g.g_k);
+}
+template <typename C, typename T, int KC> IRB_HD void coop_reduce(LobeGrads<T, KC>& g) {
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+        C::reduce(g.U[k]); C::reduce(g.V[k]); C::reduce(g.S[k]);
+        C::reduce(g.mx[k]); C::reduce(g.my[k]); C::reduce(g.mz[k]);
+    }
+}
+
 // ---- forward: out_diff, out_spec --------------------------------------------------------
-template <typename T, int KC>
+template <typename T, int KC, typename Coop = Solo>
 IRB_HD void drv_render_sg_fwd(const RenderSgArgs& ai, const PixView& vi, const RenderSgArgs& a, const PixView& vo, const EnvTab& tab) {
     Pixel<T> px;
     V3<T> nt;
@@ -102,9 +124,11 @@ IRB_HD void drv_render_sg_fwd(const RenderSgArgs& ai, const PixView& vi, const R
         Lobes<T, KC> L;
         load_lobes(L, ai, vi.b, vi.pix, vi.plane, k0);
         T U[KC], V[KC];
-        sweep_fwd<T, KC>(px, L, tab, U, V);
+        sweep_fwd<T, KC>(px, L, tab, U, V, Coop::slice());
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
+            Coop::reduce(U[k]);
+            Coop::reduce(V[k]);
             if (k0 + k < ai.K) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -115,6 +139,7 @@ IRB_HD void drv_render_sg_fwd(const RenderSgArgs& ai, const PixView& vi, const R
             }
         }
     }
+    if (!Coop::leader()) return;
     const size_t o3 = (vo.b * 3) * vo.plane + vo.pix;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -184,7 +209,7 @@ IRB_HD void store_lobe_grads(const LobeGrads<T, KC>& lg, const Lobes<T, KC>& L, 
     }
 }
 
-template <typename T, int KP, int KL, bool PIX, bool LOBE>
+template <typename T, int KP, int KL, bool PIX, bool LOBE, typename Coop = Solo>
 IRB_HD void drv_render_sg_bwd(const RenderSgArgs& ai, const PixView& vi, const RenderSgArgs& a, const PixView& vo, const EnvTab& tab) {
     Pixel<T> px;
     V3<T> nt;
@@ -210,8 +235,10 @@ IRB_HD void drv_render_sg_bwd(const RenderSgArgs& ai, const PixView& vi, const R
         T P[KP], Q[KP];
         load_PQ<T, KP>(P, Q, ai, vi.b, vi.pix, vi.plane, 0, gDa, gS);
         LobeGrads<T, KP> lg;
-        sweep_bwd<T, KP, PIX, LOBE>(px, L, P, Q, tab, pg, lg);
-        if (LOBE) store_lobe_grads<T, KP>(lg, L, P, Q, ai, vi, a, vo, 0, gDa, gS, gAlb);
+        sweep_bwd<T, KP, PIX, LOBE>(px, L, P, Q, tab, pg, lg, Coop::slice());
+        if (PIX) coop_reduce<Coop>(pg);
+        if (LOBE) coop_reduce<Coop>(lg);
+        if (LOBE && Coop::leader()) store_lobe_grads<T, KP>(lg, L, P, Q, ai, vi, a, vo, 0, gDa, gS, gAlb);
     } else {
         if (PIX) {
             Lobes<T, KP> L;
@@ -219,7 +246,8 @@ IRB_HD void drv_render_sg_bwd(const RenderSgArgs& ai, const PixView& vi, const R
             T P[KP], Q[KP];
             load_PQ<T, KP>(P, Q, ai, vi.b, vi.pix, vi.plane, 0, gDa, gS);
             LobeGrads<T, KP> lg;  // unused
-            sweep_bwd<T, KP, true, false>(px, L, P, Q, tab, pg, lg);
+            sweep_bwd<T, KP, true, false>(px, L, P, Q, tab, pg, lg, Coop::slice());
+            coop_reduce<Coop>(pg);
         }
         if (LOBE) {
             for (int k0 = 0; k0 < a.K; k0 += KL) {
@@ -228,11 +256,13 @@ IRB_HD void drv_render_sg_bwd(const RenderSgArgs& ai, const PixView& vi, const R
                 T P[KL], Q[KL];
                 load_PQ<T, KL>(P, Q, ai, vi.b, vi.pix, vi.plane, k0, gDa, gS);
                 LobeGrads<T, KL> lg;
-                sweep_bwd<T, KL, false, true>(px, L, P, Q, tab, pg, lg);
-                store_lobe_grads<T, KL>(lg, L, P, Q, ai, vi, a, vo, k0, gDa, gS, gAlb);
+                sweep_bwd<T, KL, false, true>(px, L, P, Q, tab, pg, lg, Coop::slice());
+                coop_reduce<Coop>(lg);
+                if (Coop::leader()) store_lobe_grads<T, KL>(lg, L, P, Q, ai, vi, a, vo, k0, gDa, gS, gAlb);
             }
         }
     }
+    if (!Coop::leader()) return;
     if (PIX) {
         V3<T> g_nt;
         T g_rough;

@@ -295,8 +295,15 @@ __device__ __forceinline__ void dir_bwd_local2(PixelGradL2& g, const Pixel<float
 }
 #endif  // __CUDACC__
 
+// The sweeps walk the directions d0, d0 + dstep, ... : (0, 1) for a thread that owns the pixel, (lane, 32) when a warp
+// shares one pixel and adds the partial sums up afterwards (every accumulator is a plain sum over directions).
+struct DirSlice {
+    int d0, dstep;
+};
+
 template <typename T, int KC>
-IRB_HD void sweep_fwd(const Pixel<T>& px, const Lobes<T, KC>& L, const EnvTab& tab, T (&U)[KC], T (&V)[KC]) {
+IRB_HD void sweep_fwd(const Pixel<T>& px, const Lobes<T, KC>& L, const EnvTab& tab, T (&U)[KC], T (&V)[KC],
+                      DirSlice sl = DirSlice{0, 1}) {
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
         U[k] = T(0);
@@ -313,7 +320,7 @@ IRB_HD void sweep_fwd(const Pixel<T>& px, const Lobes<T, KC>& L, const EnvTab& t
 #pragma unroll
             for (int i = 0; i < KC / 2; ++i) U2[i] = V2[i] = pk(0.f, 0.f);
 #pragma unroll 2
-            for (int d = 0; d < tab.D; ++d) {
+            for (int d = sl.d0; d < tab.D; d += sl.dstep) {
                 const float wx = tab.lx[d], wy = tab.ly[d], wz = tab.lz[d];
                 DirL<float> dr;
                 dir_fwd_local(dr, px, pl, wx, wy, wz);
@@ -337,7 +344,7 @@ IRB_HD void sweep_fwd(const Pixel<T>& px, const Lobes<T, KC>& L, const EnvTab& t
         }
 #endif
 #pragma unroll 2
-        for (int d = 0; d < tab.D; ++d) {
+        for (int d = sl.d0; d < tab.D; d += sl.dstep) {
             const T wx = (T)tab.lx[d], wy = (T)tab.ly[d], wz = (T)tab.lz[d];
             DirL<T> dr;
             dir_fwd_local(dr, px, pl, wx, wy, wz);
@@ -352,7 +359,7 @@ IRB_HD void sweep_fwd(const Pixel<T>& px, const Lobes<T, KC>& L, const EnvTab& t
             }
         }
     } else {
-        for (int d = 0; d < tab.D; ++d) {
+        for (int d = sl.d0; d < tab.D; d += sl.dstep) {
             const T wx = (T)tab.lx[d], wy = (T)tab.ly[d], wz = (T)tab.lz[d];
             Dir<T> dr;
             dir_fwd(dr, px, wx, wy, wz);
@@ -401,7 +408,7 @@ IRB_HD T lobes_bwd_dir(LobeGrads<T, KC>& lg, const Lobes<T, KC>& L, const T (&P)
 // this chunk); LOBE: accumulate the SG-side gradients of this chunk.
 template <typename T, int KC, bool PIX, bool LOBE>
 IRB_HD void sweep_bwd(const Pixel<T>& px, const Lobes<T, KC>& L, const T (&P)[KC], const T (&Q)[KC], const EnvTab& tab,
-                      PixelGrad<T>& pg, LobeGrads<T, KC>& lg) {
+                      PixelGrad<T>& pg, LobeGrads<T, KC>& lg, DirSlice sl = DirSlice{0, 1}) {
     if (LOBE) {
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
@@ -421,7 +428,7 @@ IRB_HD void sweep_bwd(const Pixel<T>& px, const Lobes<T, KC>& L, const T (&P)[KC
             pack_pq<KC>(P2, Q2, P, Q);
             LobeGradsPk<KC> g2;
             gradspk_zero<KC>(g2);
-            for (int d = 0; d < tab.D; ++d) {
+            for (int d = sl.d0; d < tab.D; d += sl.dstep) {
                 const float wx = tab.lx[d], wy = tab.ly[d], wz = tab.lz[d];
                 DirL<float> dr;
                 dir_fwd_local(dr, px, pl, wx, wy, wz);
@@ -434,7 +441,7 @@ IRB_HD void sweep_bwd(const Pixel<T>& px, const Lobes<T, KC>& L, const T (&P)[KC
             return;
         }
 #endif
-        for (int d = 0; d < tab.D; ++d) {
+        for (int d = sl.d0; d < tab.D; d += sl.dstep) {
             const T wx = (T)tab.lx[d], wy = (T)tab.ly[d], wz = (T)tab.lz[d];
             DirL<T> dr;
             dir_fwd_local(dr, px, pl, wx, wy, wz);
@@ -445,7 +452,7 @@ IRB_HD void sweep_bwd(const Pixel<T>& px, const Lobes<T, KC>& L, const T (&P)[KC
         }
         if (PIX) gradl_to_world(pg, gl, px);
     } else {
-        for (int d = 0; d < tab.D; ++d) {
+        for (int d = sl.d0; d < tab.D; d += sl.dstep) {
             const T wx = (T)tab.lx[d], wy = (T)tab.ly[d], wz = (T)tab.lz[d];
             Dir<T> dr;
             dir_fwd(dr, px, wx, wy, wz);

@@ -297,8 +297,7 @@ extern "C" int irb_render_sg_fwd(const float* albedo, const float* normal, const
         if (K <= 6) rc = launch_group(render_sg_group_kernel<0, 1, false, false, 4>, a, tab, false, st, w, kThreads / 1);
         else if (K <= 12) rc = launch_group(render_sg_group_kernel<0, 2, false, false, 4>, a, tab, false, st, w, kThreads / 2);
         else rc = launch_group(render_sg_group_kernel<0, 4, false, false, 4>, a, tab, false, st, w, kThreads / 4);
-        if (rc) return rc;
-        a.only_irregular = 1;  // follow-up: the clamped / degenerate pixels, general world-space path
+        return rc;   // pixels outside the regular regime were shaded inside the kernel (group_general_pixel)
     }
     const dim3 grid((unsigned)(((size_t)R * C + kThreads - 1) / kThreads), (unsigned)B);
     if (K <= 12) render_sg_fwd_kernel<12><<<grid, kThreads, 0, st>>>(a, tab);
@@ -351,8 +350,7 @@ extern "C" int irb_render_sg_bwd(const float* albedo, const float* normal, const
         else if (K <= 12) rc = IRB_GROUP_BWD(2);
         else rc = IRB_GROUP_BWD(4);
 #undef IRB_GROUP_BWD
-        if (rc) return rc;
-        a.only_irregular = 1;
+        return rc;   // pixels outside the regular regime were handled inside the kernel (group_general_pixel)
     }
     const dim3 grid((unsigned)(((size_t)R * C + kThreads - 1) / kThreads), (unsigned)B);
     if (K <= 12) {

@@ -87,7 +87,7 @@ struct TabS {
 
 // ---- one tile, forward ----------------------------------------------------------------------
 template <int TPP>
-__device__ __forceinline__ void group_tile_fwd(const RenderSgArgs& a, const RenderSgArgs& sv, const EnvTab& tab, const TabS& ts,
+__device__ __forceinline__ bool group_tile_fwd(const RenderSgArgs& a, const RenderSgArgs& sv, const EnvTab& tab, const TabS& ts,
                                                const PixView& vi, const PixView& vo, bool in_range, int h) {
     const int lane = threadIdx.x & 31, lane_base = lane - h;
     Pixel<float> px;
@@ -166,16 +166,17 @@ __device__ __forceinline__ void group_tile_fwd(const RenderSgArgs& a, const Rend
             a.out_spec[o3 + c * vo.plane] = Sc[c];
         }
     }
+    return in_range && !px.regular;
 }
 
 // ---- one tile, backward ---------------------------------------------------------------------
 template <int TPP, bool PIX, bool LOBE>
-__device__ __forceinline__ void group_tile_bwd(const RenderSgArgs& a, const RenderSgArgs& sv, const EnvTab& tab, const TabS& ts,
+__device__ __forceinline__ bool group_tile_bwd(const RenderSgArgs& a, const RenderSgArgs& sv, const EnvTab& tab, const TabS& ts,
                                                const PixView& vi, const PixView& vo, bool in_range, int h) {
     const int lane = threadIdx.x & 31, lane_base = lane - h;
     const size_t i3 = (vi.b * 3) * vi.plane + vi.pix;
     float gD[3], gS[3], gDa[3];
-    bool active;
+    bool active, irregular;
     PixelGradL<float> gl;
     pixel_gradl_zero(gl);
     LobeGrads<float, kLPT> lg;
@@ -187,6 +188,7 @@ __device__ __forceinline__ void group_tile_bwd(const RenderSgArgs& a, const Rend
         float A[3];
         load_pixel(px, nt, A, sv, vi.b, vi.pix, vi.plane);
         active = in_range && px.regular;
+        irregular = in_range && !px.regular;
         PixelLocal<float> pl;
         pixel_local_setup(pl, px);
 #pragma unroll
@@ -309,11 +311,41 @@ __device__ __forceinline__ void group_tile_bwd(const RenderSgArgs& a, const Rend
             if (a.g_rough) a.g_rough[vo.b * vo.plane + vo.pix] = g_rough;
         }
     }
+    return irregular;
+}
+
+// ---- pixels outside the regular regime (clamped / degenerate normals) ------------------------------------------------
+// They take the general world-space path of irb_driver.cuh -- the code of the plain kernels.  Real inputs have none or a
+// handful (pooled normals that happen to be parallel to the up vector), but one thread walking all 128 directions x K
+// lobes alone takes ~60-100 us, which a follow-up launch (or a queue drained at the end of the kernel) exposes in full.
+// So the warp that meets such a pixel shades it at once, cooperatively: every lane takes 4 of the 128 directions, the
+// partial sums are added across the warp, lane 0 stores (a few microseconds, inside a kernel that runs for a millisecond).
+// __noinline__: the general path gets its own register allocation instead of inflating the fast path's.
+struct WarpCoop {
+    __device__ static DirSlice slice() { return DirSlice{(int)(threadIdx.x & 31), 32}; }
+    __device__ static void reduce(float& v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    __device__ static bool leader() { return (threadIdx.x & 31) == 0; }
+};
+
+template <int MODE, bool PIX, bool LOBE>
+__device__ __noinline__ void group_general_pixel(const RenderSgArgs& a, const EnvTab& tab, unsigned gidx) {
+    const size_t plane = (size_t)a.R * a.C;
+    const PixView v{(size_t)gidx / plane, (size_t)gidx % plane, plane};
+    if (MODE == 0) {
+        if (a.K <= 12) drv_render_sg_fwd<float, 12, WarpCoop>(a, v, a, v, tab);
+        else drv_render_sg_fwd<float, 24, WarpCoop>(a, v, a, v, tab);
+    } else {
+        if (a.K <= 12) drv_render_sg_bwd<float, 12, 12, PIX, LOBE, WarpCoop>(a, v, a, v, tab);
+        else drv_render_sg_bwd<float, 24, 12, PIX, LOBE, WarpCoop>(a, v, a, v, tab);
+    }
 }
 
 // MODE 0 forward, 1 backward
 template <int MODE, int TPP, bool PIX, bool LOBE, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) render_sg_group_kernel(const RenderSgArgs a, const __grid_constant__ EnvTab tab,
+__global__ void __launch_bounds__(kThreads, MINB) render_sg_group_kernel(const __grid_constant__ RenderSgArgs a, const __grid_constant__ EnvTab tab,
                                                                           const __grid_constant__ TileMaps maps,
                                                                           const unsigned total_tiles, const unsigned tiles_per_img) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -361,9 +393,17 @@ __global__ void __launch_bounds__(kThreads, MINB) render_sg_group_kernel(const R
         const RenderSgArgs sv = stage_view_n(a, cur, PT);
         const PixView vi{0, (size_t)q, (size_t)PT};
         const PixView vo{b, pix0 + q, plane};
-        if (MODE == 0) group_tile_fwd<TPP>(a, sv, tab, ts, vi, vo, in_range, h);
-        else group_tile_bwd<TPP, PIX, LOBE>(a, sv, tab, ts, vi, vo, in_range, h);
+        bool irr;
+        if (MODE == 0) irr = group_tile_fwd<TPP>(a, sv, tab, ts, vi, vo, in_range, h);
+        else irr = group_tile_bwd<TPP, PIX, LOBE>(a, sv, tab, ts, vi, vo, in_range, h);
         mbar_arrive(&empty_bar[s]);   // this thread is done with stage s
+        unsigned m = __ballot_sync(0xffffffffu, irr && h == 0);
+        while (m) {   // rare: the whole warp shades each such pixel through the general path
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const unsigned g = __shfl_sync(0xffffffffu, (unsigned)(b * plane + pix0 + q), src);
+            group_general_pixel<MODE, PIX, LOBE>(a, tab, g);
+        }
     }
 }
 
