@@ -18,6 +18,11 @@
 // (3 FMA, no separate multiply) and  sum_d T (a.w - 1) = (sum_d T arg) / lam'.
 #pragma once
 #include "irb_math.cuh"
+#if defined(__CUDACC__)
+// the generic (host / double) loops behind the `if constexpr` device-float branches are dead code in float device
+// instantiations by design
+#pragma nv_diag_suppress 128
+#endif
 
 namespace irb {
 

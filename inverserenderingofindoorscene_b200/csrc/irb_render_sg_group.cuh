@@ -9,10 +9,10 @@
 //     broadcasts spec_d with one warp shuffle; every lane runs its 6 lobes for all directions;
 //   * the per-direction  sum_k Q_k e_kd  is completed across the group with a shuffle reduce-scatter;
 //   * per-pixel results (diffuse/spec, d/dnormal, d/drough, d/dalbedo) are butterfly-reduced once per pixel.
-// Same staging as irb_render_sg.cu: persistent CTAs, 2-stage cp.async.bulk + mbarrier ring, tile =
-// 128/TPP pixels.  Only pixels in the regular regime (irb_math.cuh) are handled here; the (rare)
-// clamped / degenerate ones are left to a follow-up launch of the plain kernel with only_irregular = 1,
-// which evaluates the general world-space path exactly as before.
+// Staging: persistent CTAs, 2-stage ring filled by tiled TMA (one cp.async.bulk.tensor per tensor) with full/empty
+// mbarriers, tile = 128/TPP pixels.  The lobe-split fast path covers pixels in the regular regime (irb_math.cuh); the
+// (rare) clamped / degenerate ones are shaded on the spot by the whole warp through the general world-space path of
+// irb_driver.cuh (group_general_pixel below).
 #pragma once
 
 namespace irb {

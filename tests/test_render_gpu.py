@@ -307,7 +307,7 @@ def test_trainlight_loss_step_vs_oracle(irb):
 @pytest.mark.parametrize('K', [1, 5, 6, 7, 12, 13, 24])
 def test_lobe_counts_group_kernels(irb, K):
     """every lobe-split configuration (TPP = 1, 2, 4; padded last group) against the fp64 oracle, with a few
-    irregular pixels mixed in (handled by the follow-up launch)"""
+    irregular pixels mixed in (shaded by the warp-cooperative general path inside the kernels)"""
     from oracle import render_oracle as ro
     B, R, C = 2, 8, 12
     ins64 = ro.synth_inputs(B, R, C, R, C, K, seed=500 + K, dtype=torch.float64, hi=0.95)
