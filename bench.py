@@ -407,8 +407,8 @@ def run_ours(args):
         flop_bwd = 128 * 250 * 2.0 * npx
         fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6
         # DRAM traffic of the backward kernel from the committed ncu --set full capture of this config
-        # (profiles/r01/ncu_v8_bwd_summary.txt: dram read 481.1 MB + write 408.5 MB per launch)
-        traffic_bwd = 481.134592e6 + 408.537856e6 if (B, H, W, K) == (16, 240, 320, 12) else None
+        # (profiles/r01/ncu_v9_bwd_summary.txt: dram read 483.7 MB + write 407.2 MB per launch)
+        traffic_bwd = 483.660800e6 + 407.164416e6 if (B, H, W, K) == (16, 240, 320, 12) else None
         line = {
             'metric': 'Mpixels/s render-layer fwd+bwd (240x320, 12 SG)', 'value': value, 'unit': 'Mpix/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_step,
@@ -420,7 +420,7 @@ def run_ours(args):
             'kernel_ms': {'render_sg_fwd': fwd_ms, 'render_sg_bwd': bwd_ms},
             'roofline': {'bound': 'hbm', 'kernel': 'render_sg_group_kernel<1,2,1,1,2> (fused backward, lobe-split)', 'achieved': ach,
                          'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': traffic_bwd,
-                         'traffic_source': 'profiles/r01/ncu_v8_bwd_summary.txt: ncu --set full, dram__bytes_read+write per launch',
+                         'traffic_source': 'profiles/r01/ncu_v9_bwd_summary.txt: ncu --set full, dram__bytes_read+write per launch',
                          'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': bwd_bytes,
                          'fwd': {'achieved': fwd_bytes / (fwd_ms * 1e-3) / 1e9, 'algorithmic_bytes_per_launch': fwd_bytes},
