@@ -32,7 +32,6 @@ struct RenderSgArgs {
     int B, K, R, C;
     float F0;
     int warp;
-    int only_irregular;  // 1: this launch only handles pixels whose normal/frame is NOT in the regular regime
 };
 
 template <typename T, int KC>
@@ -118,7 +117,6 @@ IRB_HD void drv_render_sg_fwd(const RenderSgArgs& ai, const PixView& vi, const R
     V3<T> nt;
     T A[3];
     load_pixel(px, nt, A, ai, vi.b, vi.pix, vi.plane);
-    if (a.only_irregular && px.regular) return;
     T Dc[3] = {0, 0, 0}, Sc[3] = {0, 0, 0};
     for (int k0 = 0; k0 < ai.K; k0 += KC) {
         Lobes<T, KC> L;
@@ -215,7 +213,6 @@ IRB_HD void drv_render_sg_bwd(const RenderSgArgs& ai, const PixView& vi, const R
     V3<T> nt;
     T A[3];
     load_pixel(px, nt, A, ai, vi.b, vi.pix, vi.plane);
-    if (a.only_irregular && px.regular) return;
     const size_t i3 = (vi.b * 3) * vi.plane + vi.pix;
     const size_t o3 = (vo.b * 3) * vo.plane + vo.pix;
     T gD[3], gS[3], gDa[3];

@@ -236,10 +236,10 @@ static int launch_group(KernelT kernel, const RenderSgArgs& a, const EnvTab& tab
     return check_launch(what);
 }
 
-// Kernel variant.  Measured on B200 (profiles/r01, config 2): lobe-split "group" kernels 1.03 ms fwd / 2.26 ms bwd,
+// Kernel variant.  Measured on B200 (profiles/r01, config 2, fwd / bwd): lobe-split "group" kernels 0.82 / 1.88 ms,
 // single-thread-per-pixel staged "tma1" 1.10 / 2.38 ms, plain (no staging) 1.23 / 3.41 ms -> group is the default.
 // IRB_RENDER_VARIANT = group | tma1 | plain overrides it (A/B runs and tests).
-//   returns 0 = group (+ irregular-pixel follow-up), 1 = tma1, 2 = plain
+//   returns 0 = group, 1 = tma1, 2 = plain
 static int render_variant(bool bwd, int K) {
     (void)bwd;
     (void)K;

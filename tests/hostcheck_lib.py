@@ -24,14 +24,15 @@ class RenderSgArgs(C.Structure):
     _fields_ = [(n, FP) for n in ('albedo', 'normal', 'rough', 'axis', 'lamb', 'weight', 'view', 'out_diff',
                                   'out_spec', 'g_diff', 'g_spec', 'g_albedo', 'g_normal', 'g_rough', 'g_axis',
                                   'g_lamb', 'g_weight')] + \
-               [('B', C.c_int), ('K', C.c_int), ('R', C.c_int), ('C', C.c_int), ('F0', C.c_float), ('warp', C.c_int),
-                ('only_irregular', C.c_int)]
+               [('B', C.c_int), ('K', C.c_int), ('R', C.c_int), ('C', C.c_int), ('F0', C.c_float), ('warp', C.c_int)]
 
 
 class SgEnvArgs(C.Structure):
     _fields_ = [(n, FP) for n in ('axis', 'lamb', 'weight', 'env', 'lamb_w', 'weight_w', 'g_env', 'g_axis',
                                   'g_lamb', 'g_weight')] + \
-               [('B', C.c_int), ('K', C.c_int), ('R', C.c_int), ('C', C.c_int), ('warp', C.c_int)]
+               [('B', C.c_int), ('K', C.c_int), ('R', C.c_int), ('C', C.c_int), ('warp', C.c_int),
+                # fused reconstruction-loss fields (device kernels only; unused by the host check)
+                ('env_gt', FP), ('seg', FP), ('stats', C.POINTER(C.c_double)), ('g_num', FP), ('offset', C.c_float)]
 
 
 class RenderEnvArgs(C.Structure):
