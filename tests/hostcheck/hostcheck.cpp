@@ -61,5 +61,7 @@ int hc_render_env_bwd(int dbl, const RenderEnvArgs* s, const EnvTab* tab) {
     return 0;
 }
 size_t hc_sizeof_render_sg_args() { return sizeof(RenderSgArgs); }
+size_t hc_sizeof_sg_env_args() { return sizeof(SgEnvArgs); }
+size_t hc_sizeof_render_env_args() { return sizeof(RenderEnvArgs); }
 size_t hc_sizeof_envtab() { return sizeof(EnvTab); }
 }

@@ -56,6 +56,9 @@ def load():
     assert lib.hc_sizeof_envtab() == C.sizeof(EnvTab)
     lib.hc_sizeof_render_sg_args.restype = C.c_size_t
     assert lib.hc_sizeof_render_sg_args() == C.sizeof(RenderSgArgs)
+    for fn, st in ((lib.hc_sizeof_sg_env_args, SgEnvArgs), (lib.hc_sizeof_render_env_args, RenderEnvArgs)):
+        fn.restype = C.c_size_t
+        assert fn() == C.sizeof(st), st.__name__
     return lib
 
 
