@@ -166,3 +166,35 @@ def test_edge_cases_math(lib, dbl):
     for o, t, name in zip(outs, g64, ('albedo', 'normal', 'rough', 'axis', 'lamb', 'weight')):
         assert np.isfinite(o).all(), name
         assert relerr(o, t.numpy()) <= tol, name
+
+
+@pytest.mark.parametrize('path', RENDER, ids=[os.path.basename(q) for q in RENDER])
+def test_warp_cooperative_general_path(lib, path):
+    """The in-kernel path for pixels outside the regular regime gives every lane of a warp a slice of the directions
+    (DirSlice{lane, 32}), sums the partial accumulators across the warp (Coop::reduce) and lets one lane store
+    (irb_render_sg_group.cuh).  tests/hostcheck emulates the 32 lanes on the host in double through the same drivers:
+    the result must equal the one-thread-per-pixel run, for regular and general-path pixels alike."""
+    z = dict(np.load(path))
+    B, H, W, R, Cc, K = [int(x) for x in z['meta']]
+    ls, ew = ro.env_table()
+    tab = hc.make_tab(ls, ew)
+    alb, nrm, rg = _pooled(z)
+    view = np.ascontiguousarray(z['v'][0])
+    axis, lamb, weight = z['axis'], z['lamb'], z['weight']
+
+    def run(fwd, bwd):
+        outs = [np.zeros((B, 3, R, Cc), np.float32) for _ in range(4)] + [np.zeros((B, 1, R, Cc), np.float32),
+                                                                         np.zeros_like(axis), np.zeros_like(lamb),
+                                                                         np.zeros_like(weight)]
+        od, os_, g_alb, g_nrm, g_rg, g_ax, g_lam, g_wt = outs
+        a = hc.RenderSgArgs(hc.p(alb), hc.p(nrm), hc.p(rg), hc.p(axis), hc.p(lamb), hc.p(weight), hc.p(view),
+                            hc.p(od), hc.p(os_), hc.p(z['gD']), hc.p(z['gS']), hc.p(g_alb), hc.p(g_nrm), hc.p(g_rg),
+                            hc.p(g_ax), hc.p(g_lam), hc.p(g_wt), B, K, R, Cc, 0.05, 1)
+        assert fwd(C.byref(a), C.byref(tab)) == 0
+        assert bwd(C.byref(a), C.byref(tab)) == 0
+        return outs
+    solo = run(lambda a, t: lib.hc_render_sg_fwd(1, a, t), lambda a, t: lib.hc_render_sg_bwd(1, a, t))
+    coop = run(lib.hc_render_sg_fwd_coop, lib.hc_render_sg_bwd_coop)
+    for s_, c_, name in zip(solo, coop, ('diff', 'spec', 'g_albedo', 'g_normal', 'g_rough', 'g_axis', 'g_lamb', 'g_weight')):
+        assert np.isfinite(c_).all(), name
+        assert relerr(c_, s_) <= 1e-6, name   # fp32 storage of the outputs; the arithmetic is double in both runs
