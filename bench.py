@@ -30,6 +30,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 B_PER_GPU, H, W, K = 16, 240, 320, 12
+METRIC = 'Mpixels/s render-layer fwd+bwd (240x320, 12 SG)'
 ENV_H, ENV_W = 8, 16
 
 
@@ -40,6 +41,7 @@ def parse():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the secondary configs (bilateral, config 3/5, torch-CUDA reference)')
     ap.add_argument('--cpu-baseline-rows', type=int, default=0, help='rows of the 240x320 frame for the CPU sample (0=auto)')
     return ap.parse_args()
 
@@ -81,84 +83,92 @@ def synth(B, Hh, Ww, Kk, seed, device=None, pinned=False):
 
 
 # -------------------------------------------------------------------------------------------
-# CPU arm: the oracle port (restatement of the reference's PyTorch op graph) on host cores
+# CPU arm: the reference's OWN render layer (baseline/_ref = unmodified copy of the reference's *.py, imported by
+# oracle/ref_loader.py; kind "reference") on host cores -- or, if that copy is absent, the oracle port (kind "port").
+# One step = output2env.output2env + renderingLayer.forwardEnv + autograd backward (all six input gradients) over a
+# ROWS x 320 crop of one 240x320 frame (pixels are independent; the crop keeps the full frame's view vectors).
+# Thread count and sample are FIXED (not probed) so that every CPU figure of a round is taken the same way.
 # -------------------------------------------------------------------------------------------
 
+CPU_THREADS = 32          # torch CPU elementwise ops on these tensors stop scaling around 16-32 threads (profiles/r01)
+CPU_ROWS = 64             # cpu_baseline sample: 64 x 320 pixels per step
+
+
+def cpu_threads():
+    n = min(CPU_THREADS, os.cpu_count() or 1)
+    torch.set_num_threads(n)
+    return n
+
+
 def cpu_step_fn(rows):
-    from oracle import render_oracle as ro
+    """returns (step, kind)"""
+    from oracle import ref_loader
     ins = synth(1, rows, W, K, seed=1234 + 1)
     leaves = [t.clone().requires_grad_(True) for t in ins[:6]]
     gD, gS = ins[6], ins[7]
-    # the full-frame camera rays, cropped to the sampled rows (pixels are independent)
-    v_full = torch.from_numpy(ro.camera_rays(H, W))[:, :rows].contiguous()
+    from oracle import render_oracle as ro
+    v_full = torch.from_numpy(ro.camera_rays(H, W))[:, :rows].contiguous()   # [3,rows,W] of the full 240x320 frame
+    if ref_loader.available():
+        ref = ref_loader.load('models')
+        rl = ref.renderingLayer(imWidth=W, imHeight=rows, isCuda=False)
+        rl.v = v_full.unsqueeze(0)                       # public attribute (models.py:432): crop of the full frame's rays
+        o2e = ref.output2env(K, isCuda=False)
+        kind = 'reference'
 
-    def render(alb, nrm, rg, ax, lam, wt):
-        env, _, _, _ = ro.output2env(ax, lam, wt)
-        return ro.render_env(alb, nrm, rg, env, view=v_full)
+        def render(alb, nrm, rg, ax, lam, wt):
+            env, _, _, _ = o2e.output2env(ax, lam, wt)
+            return rl.forwardEnv(alb, nrm, rg, env)
+    else:
+        kind = 'port'
+
+        def render(alb, nrm, rg, ax, lam, wt):
+            env, _, _, _ = ro.output2env(ax, lam, wt)
+            return ro.render_env(alb, nrm, rg, env, view=v_full)
 
     def step():
         d, s = render(*leaves)
         torch.autograd.grad((d * gD).sum() + (s * gS).sum(), leaves)
-    return step
+    return step, kind
 
 
-def _best_threads(cores):
-    """torch CPU elementwise ops stop scaling (and can collapse) at high thread counts on medium tensors:
-    probe a 48-row sample at a few thread counts and keep the fastest -- the baseline gets its best setting."""
-    best, best_t = None, 1e30
-    step = cpu_step_fn(48)
-    for n in sorted(set([min(cores, x) for x in (4, 8, 16, 32, 64, cores)])):
-        torch.set_num_threads(n)
-        step()
-        t0 = time.perf_counter()
-        step()
-        t = time.perf_counter() - t0
-        if t < best_t:
-            best, best_t = n, t
-        elif t > 1.25 * best_t:
-            break  # past the scaling knee: more threads only get slower (they collapse at 100+ threads)
-    torch.set_num_threads(best)
-    return best, best_t / 48
+def _cpu_sample_text(kind, rows, threads):
+    what = ('the reference itself: baseline/_ref/models.py output2env.output2env + renderingLayer.forwardEnv + autograd'
+            if kind == 'reference' else 'oracle port (oracle/render_oracle.py restatement of the same op graph)')
+    return ('%s, fp32 fwd+bwd all grads, %d x %d pixels of one 240x320 frame per step, 12 SG, torch %s CPU, %d threads '
+            '(fixed; host has %d cores)' % (what, rows, W, torch.__version__, threads, os.cpu_count() or 1))
 
 
-def cpu_baseline(budget_s=20.0, rows=0):
-    """Time the oracle port on a bounded sample (rows x 320 pixels of one 240x320 frame)."""
-    cores = os.cpu_count() or 1
-    threads, per_row = _best_threads(cores)
-    if rows <= 0:
-        rows = int(max(48, min(H, budget_s / 3.0 / max(per_row, 1e-6))))
-    step = cpu_step_fn(rows)
-    step()  # warm-up
+def cpu_baseline(rows=0):
+    """bounded sample of config 2's workload on the host: best of 2 steps after 1 warm-up"""
+    threads = cpu_threads()
+    rows = rows if rows > 0 else CPU_ROWS
+    step, kind = cpu_step_fn(rows)
+    step()
     ts = []
     for _ in range(2):
         t0 = time.perf_counter()
         step()
         ts.append(time.perf_counter() - t0)
-    t = sorted(ts)[0]
-    return {'value': rows * W / t / 1e6, 'unit': 'Mpix/s', 'cores': threads, 'kind': 'port',
-            'sample': 'oracle/render_oracle.py fp32 fwd+bwd, %d x %d pixels of one 240x320 frame, 12 SG, '
-                      'torch %s CPU, %d threads (best of a probe over <=%d host cores), best of 2 after 1 warm-up'
-                      % (rows, W, torch.__version__, threads, cores)}
+    t = min(ts)
+    return {'value': rows * W / t / 1e6, 'unit': 'Mpix/s', 'cores': threads, 'kind': kind,
+            'sample': _cpu_sample_text(kind, rows, threads) + ', best of 2 after 1 warm-up'}
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    threads, per_row = _best_threads(cores)
-    # size the per-step sample so that the (steps+warmup) steps end within ~90 s: first guess from the thread probe,
-    # then one calibration step at that size (the probe's small samples under-estimate the per-row cost by ~2x)
+    threads = cpu_threads()
+    # per-step sample sized so that (steps + warmup) steps end within ~100 s, from one calibration step at CPU_ROWS
     nstep = max(1, args.steps + args.warmup)
-    rows = int(max(8, min(H, 90.0 / nstep / max(per_row, 1e-6))))
-    step = cpu_step_fn(rows)
+    step, kind = cpu_step_fn(CPU_ROWS)
+    step()
     t0 = time.perf_counter()
     step()
-    per_row = (time.perf_counter() - t0) / rows
-    rows2 = int(max(8, min(H, 90.0 / nstep / max(per_row, 1e-6))))
-    if rows2 != rows:
-        rows = rows2
-        step = cpu_step_fn(rows)
+    per_row = (time.perf_counter() - t0) / CPU_ROWS
+    rows = int(max(8, min(H, 100.0 / nstep / max(per_row, 1e-6))))
+    if rows != CPU_ROWS:
+        step, kind = cpu_step_fn(rows)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -166,16 +176,16 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     val = rows * W * args.steps / dt / 1e6
-    sample = ('oracle port (restatement of models.output2env + renderingLayer.forwardEnv + autograd), fp32, '
-              '%d x %d pixels of one 240x320 frame per step, %d threads (best of a probe over <=%d host cores)'
-              % (rows, W, threads, cores))
+    sample = _cpu_sample_text(kind, rows, threads)
     print(json.dumps({
-        'impl': 'reference', 'metric': 'Mpixels/s render-layer fwd+bwd (240x320, 12 SG)', 'value': val,
+        'impl': 'reference', 'metric': METRIC, 'value': val,
         'unit': 'Mpix/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'config2: fused SG render fwd+bwd, 240x320, 12 SG (CPU sample: %d rows)' % rows},
-        'cpu_baseline': {'value': val, 'unit': 'Mpix/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+        'config': {'workload': 'config2: SG render layer fwd+bwd (output2env.output2env -> renderingLayer.forwardEnv), '
+                               '240x320, 12 SG, all input grads; CPU sample: %d rows of one frame per step (per-pixel '
+                               'rate: pixels are independent)' % rows},
+        'cpu_baseline': {'value': val, 'unit': 'Mpix/s', 'cores': threads, 'kind': kind, 'sample': sample},
         'e2e': {'value': val, 'unit': 'Mpix/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}))
 
@@ -263,12 +273,93 @@ class Clocks(threading.Thread):
 # ours
 # -------------------------------------------------------------------------------------------
 
+def ncu_metrics():
+    """per-kernel counters of the last `python bench.py --profile` run on a B200 (profiles/<round>/ncu_metrics.json,
+    written by tools/ncu_profile.py from an `ncu --set full` capture of THIS bench command): DRAM traffic per launch,
+    pipe utilisations, registers.  Returns {} when no capture is committed."""
+    best = {}
+    pdir = os.path.join(ROOT, 'profiles')
+    if os.path.isdir(pdir):
+        for rnd in sorted(os.listdir(pdir)):
+            f = os.path.join(pdir, rnd, 'ncu_metrics.json')
+            if os.path.exists(f):
+                try:
+                    best = json.load(open(f))
+                    best['_file'] = os.path.relpath(f, ROOT)
+                except Exception:
+                    pass
+    return best
+
+
+def max_over_ranks(ms, dev, world):
+    import torch.distributed as dist
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def timed_ranks(step, steps, warmup, dev, world):
+    """W warm-ups, then exactly `steps` steps between barrier+synchronize pairs, CUDA events, max over ranks (ms/step)"""
+    import torch.distributed as dist
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+    for _ in range(warmup):
+        step()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    sync_all()
+    return max_over_ranks(e0.elapsed_time(e1) / steps, dev, world)
+
+
+def make_render_step(irb_models, sharding, dev, B, Hm, Wm, R, C, Kk, seed, all_grads=True):
+    """One render-loss step through the reference call pattern (wrapperBRDFLight.py:177,194-207):
+    output2env.output2env -> renderingLayer.forwardEnv -> render loss (fused LSregressDiffSpec + clamp + masked L2)
+    -> 4-float loss all-reduce (NCCL when world > 1) -> backward."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    alb = torch.rand(B, 3, Hm, Wm, device=dev, generator=g)
+    n = torch.randn(B, 3, Hm, Wm, device=dev, generator=g)
+    n[:, 2] += 1.5
+    n = n / n.norm(dim=1, keepdim=True)
+    if (Hm, Wm) == (R, C):
+        n = n * (0.7 + 0.28 * torch.rand(B, 1, Hm, Wm, device=dev, generator=g))
+    rg = torch.rand(B, 1, Hm, Wm, device=dev, generator=g) * 2 - 1
+    ax = torch.randn(B, Kk, 3, R, C, device=dev, generator=g)
+    ax = ax / ax.norm(dim=2, keepdim=True)
+    lam = torch.rand(B, Kk, R, C, device=dev, generator=g)
+    wt = torch.rand(B, 3 * Kk, R, C, device=dev, generator=g)
+    im = torch.rand(B, 3, R, C, device=dev, generator=g)
+    seg = (torch.rand(B, 1, R, C, device=dev, generator=g) > 0.2).float()
+    layer = irb_models.renderingLayer(imWidth=C, imHeight=R, isCuda=True)
+    o2e = irb_models.output2env(Kk, isCuda=True)
+    maps = (alb, n.contiguous(), rg)
+
+    def step():
+        m = [t.detach().requires_grad_(all_grads) for t in maps]
+        sg = [t.detach().requires_grad_(True) for t in (ax, lam, wt)]
+        env, _, _, _ = o2e.output2env(*sg)
+        d, s = layer.forwardEnv(m[0], m[1], m[2], env)
+        _, num, cnt, _ = irb_models.renderLossTerms(d, s, im, seg)
+        rerr, _ = sharding.sharded_losses(num, cnt, None, None)
+        rerr.backward()
+        return rerr
+    return step
+
+
 def run_ours(args):
     import torch.distributed as dist
     from inverserenderingofindoorscene_b200 import models as irb_models
-    from inverserenderingofindoorscene_b200 import _lib
+    from inverserenderingofindoorscene_b200 import _lib, sharding
 
-    _lib.lib()  # fail loudly if the CUDA library is missing
+    lib = _lib.lib()  # fail loudly if the CUDA library is missing
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -280,22 +371,32 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=dev)
     B = B_PER_GPU
     host = synth(B, H, W, K, seed=1234 + 2 + rank, pinned=True)
-    devt = [t.to(dev) for t in host]
+    gi = torch.Generator().manual_seed(99 + rank)
+    im_host = torch.rand(B, 3, H, W, generator=gi).pin_memory()
+    seg_host = (torch.rand(B, 1, H, W, generator=gi) > 0.2).float().pin_memory()
+    devt = [t.to(dev) for t in host[:6]]
+    im_d, seg_d = im_host.to(dev), seg_host.to(dev)
     layer = irb_models.renderingLayer(imWidth=W, imHeight=H, isCuda=True)
-    gD, gS = devt[6], devt[7]
+    o2e = irb_models.output2env(K, isCuda=True)
     npx = B * H * W
+    warm = max(3, args.warmup)
 
-    def step_device(ev=None):
-        leaves = [t.detach().requires_grad_(True) for t in devt[:6]]
+    # The step, through the REFERENCE call pattern (wrapperBRDFLight.py:177,194-207): output2env.output2env (lazy env-map,
+    # never written because forwardEnv is its only consumer) -> renderingLayer.forwardEnv (fused kernel) -> render loss
+    # (irb_render_loss: LSregressDiffSpec + clamp + masked L2, device-side pixelNum) -> the path's ONE exchange, the
+    # 4-float loss all-reduce (NCCL at N > 1) -> backward (loss seed kernel + fused render backward, all six input grads).
+    def step_device(ins, im, seg, ev=None):
+        leaves = [t.detach().requires_grad_(True) for t in ins]
         if ev:
             ev[0].record()
-        d, s = layer.forwardSG(*leaves)
+        env, _, _, _ = o2e.output2env(leaves[3], leaves[4], leaves[5])
+        d, s = layer.forwardEnv(leaves[0], leaves[1], leaves[2], env)
         if ev:
             ev[1].record()
-        torch.autograd.backward([d, s], [gD, gS])
-        if ev:
-            ev[2].record()
-        return d, s, leaves
+        rend, num, cnt, _ = irb_models.renderLossTerms(d, s, im, seg)
+        rerr, _ = sharding.sharded_losses(num, cnt, None, None)
+        rerr.backward()
+        return rend, rerr, leaves
 
     def sync_all():
         torch.cuda.synchronize()
@@ -304,46 +405,46 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     # ---- value: device-resident inputs -------------------------------------------------------
-    for _ in range(max(3, args.warmup)):
-        step_device()
+    for _ in range(warm):
+        step_device(devt, im_d, seg_d)
     sync_all()
     clocks = Clocks(local)
     clocks.start()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+    sink = []
+    irb_models._EVENT_SINK = sink          # the fused backward kernel brackets itself with CUDA events on its stream
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    l0 = lib.irb_launch_count()
     e0.record()
     for i in range(args.steps):
-        step_device(evs[i])
+        step_device(devt, im_d, seg_d, evs[i])
     e1.record()
     sync_all()
+    launches = lib.irb_launch_count() - l0
+    irb_models._EVENT_SINK = None
     clocks.stop_flag = True
-    ms_total = e0.elapsed_time(e1)
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps, dev, world)
     fwd_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
-    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_step = ms_total / args.steps
+    bwd_evs = [x for x in sink if x[0] == 'render_sg_bwd']
+    bwd_ms = sum(x[1].elapsed_time(x[2]) for x in bwd_evs) / max(1, len(bwd_evs))
     value = world * npx / (ms_step * 1e-3) / 1e6
 
-    # ---- e2e: pinned host buffers -> public API -> loss + rendered image back to host ---------
+    # ---- e2e: pinned host buffers -> public API -> loss terms + rendered image back to host ---------
     # Every step copies ITS inputs host->device and reads ITS results back; like any production feeder the copies
     # of step i+1 run on a second stream while step i computes (double-buffered device inputs).
-    im = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(99)).pin_memory()
     out_host = torch.empty(B, 3, H, W).pin_memory()
-    loss_host = torch.empty(4).pin_memory()
-    npx_t = torch.tensor(float(npx), device=dev)
+    loss_host = torch.empty(1).pin_memory()
     copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [[torch.empty_like(h, device=dev) for h in host[:6]] + [torch.empty_like(im, device=dev)] for _ in range(2)]
+    srcs = list(host[:6]) + [im_host, seg_host]
+    bufs = [[torch.empty_like(h, device=dev) for h in srcs] for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     freed = [torch.cuda.Event(), torch.cuda.Event()]
 
     def upload(slot):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(freed[slot])          # the compute stream is done with this slot
-            for dst, src in zip(bufs[slot], list(host[:6]) + [im]):
+            for dst, src in zip(bufs[slot], srcs):
                 dst.copy_(src, non_blocking=True)
             ready[slot].record(copy_stream)
 
@@ -352,23 +453,10 @@ def run_ours(args):
         cur.wait_event(ready[slot])
         if prefetch:
             upload(slot ^ 1)
-        ins = [t.detach().requires_grad_(True) for t in bufs[slot][:6]]
-        imd = bufs[slot][6]
-        d, s = layer.forwardSG(*ins)
-        rend = torch.clamp(d + s, 0, 1)
-        diff = rend - imd
-        part = torch.stack([(diff * diff).sum(), npx_t, d.detach().sum(), s.detach().sum()])
-        if world > 1:
-            red = part.detach().clone()
-            dist.all_reduce(red)           # the path's one exchange step: 4-float loss all-reduce
-            loss = part[0] / red[1] / 3.0
-        else:
-            red = part.detach()
-            loss = part[0] / part[1] / 3.0
-        loss.backward()
+        rend, rerr, _ = step_device(bufs[slot][:6], bufs[slot][6], bufs[slot][7])
         freed[slot].record(cur)
-        out_host.copy_(rend.detach(), non_blocking=True)
-        loss_host.copy_(red, non_blocking=True)
+        out_host.copy_(rend, non_blocking=True)
+        loss_host.copy_(rerr.detach().reshape(1), non_blocking=True)
         cur.synchronize()                  # the step's results are on the host
         return float(loss_host[0])
 
@@ -386,13 +474,18 @@ def run_ours(args):
     run_e2e(n_e2e)
     e1.record()
     sync_all()
-    e2e_ms = e0.elapsed_time(e1) / n_e2e
-    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-    h2d = sum(h.numel() * 4 for h in host[:6]) + im.numel() * 4
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1) / n_e2e, dev, world)
+    h2d = sum(h.numel() * 4 for h in srcs)
     d2h = out_host.numel() * 4 + loss_host.numel() * 4
+
+    # ---- the other BASELINE configs that run on this many GPUs (extras; not the headline) --------------
+    extras = {}
+    if not args.no_extras:
+        import bench_configs as bc
+        try:
+            extras = bc.extras_for_bench(irb_models, sharding, dev, rank, world, timed_ranks, make_render_step)
+        except Exception as ex:   # extras never take the headline down
+            extras = {'error': repr(ex)}
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -400,46 +493,49 @@ def run_ours(args):
         fwd_bytes = (13 + 7 * K) * 4 * npx       # reads 7+7K, writes 6
         ach = bwd_bytes / (bwd_ms * 1e-3) / 1e9
         clk = clocks.summary()
-        sm_mhz = clk.get('sm_mhz') or 1965
-        # instruction model read off the SASS of the two kernels (profiles/r01): FMA-pipe instructions per pixel
-        # and direction -- forward 12 lobes x 5 + ~50 BRDF = 110, backward 12 x 13 + ~95 = 250; 2 FLOP each
-        flop_fwd = 128 * 110 * 2.0 * npx
-        flop_bwd = 128 * 250 * 2.0 * npx
-        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6
-        # DRAM traffic of the backward kernel from the committed ncu --set full capture of this config
-        # (profiles/r01/ncu_v9_bwd_summary.txt: dram read 483.7 MB + write 407.2 MB per launch)
-        traffic_bwd = 483.660800e6 + 407.164416e6 if (B, H, W, K) == (16, 240, 320, 12) else None
+        nm = ncu_metrics()
+        kb = nm.get('render_sg_bwd', {})
+        kf = nm.get('render_sg_fwd', {})
         line = {
-            'metric': 'Mpixels/s render-layer fwd+bwd (240x320, 12 SG)', 'value': value, 'unit': 'Mpix/s',
-            'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup), 'ms_per_step': ms_step,
+            'metric': METRIC, 'value': value, 'unit': 'Mpix/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': warm, 'ms_per_step': ms_step,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'config2: fused SG render fwd+bwd (models.renderingLayer.forwardSG), '
-                                   'batch 16 per GPU x 240x320, 12 SG, all input grads',
+            'config': {'workload': 'config2: SG render layer fwd+bwd through the reference call pattern '
+                                   'models.output2env.output2env -> models.renderingLayer.forwardEnv (lazy env-map, fused '
+                                   'kernel) + fused render loss + 4-float loss all-reduce + backward, batch 16 per GPU x '
+                                   '240x320, 12 SG, all six input grads',
                        'global_batch': B * world, 'grid': [H, W], 'sg_lobes': K, 'parallelism': 'batch-shard x%d' % world,
+                       'collective': 'one 4-float all-reduce per step inside the timed region (NCCL)' if world > 1
+                                     else 'none at N=1 (same code path, world size 1)',
                        'l2': 'inputs per step (447 MB/GPU) exceed the 126 MB L2; no explicit flush'},
-            'kernel_ms': {'render_sg_fwd': fwd_ms, 'render_sg_bwd': bwd_ms},
-            'roofline': {'bound': 'hbm', 'kernel': 'render_sg_group_kernel<1,2,1,1,2> (fused backward, lobe-split)', 'achieved': ach,
-                         'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': traffic_bwd,
-                         'traffic_source': 'profiles/r01/ncu_v9_bwd_summary.txt: ncu --set full, dram__bytes_read+write per launch',
+            'kernel_ms': {'render_sg_fwd': fwd_ms, 'render_sg_bwd': bwd_ms,
+                          'loss_allreduce_seed_and_host_gaps': ms_step - fwd_ms - bwd_ms},
+            'roofline': {'bound': 'hbm', 'binding_resource': 'fp32 FMA pipe (compute-bound kernel, ~70 FLOP/B; DESIGN.md 4.1)',
+                         'kernel': 'render_sg_group_kernel<1,...> (fused backward, lobe-split)', 'achieved': ach,
+                         'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+                         'traffic': kb.get('dram_bytes'), 'traffic_source': nm.get('_file'),
                          'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': bwd_bytes,
-                         'fwd': {'achieved': fwd_bytes / (fwd_ms * 1e-3) / 1e9, 'algorithmic_bytes_per_launch': fwd_bytes},
-                         'fp32': {'note': 'kernel is FP32-FMA/MUFU bound, not HBM bound (DESIGN.md 4.1): FMA-pipe '
-                                          'instruction model x 2 FLOP vs 148 SM x 128 lanes x 2 x sm clock',
-                                  'bwd_tflops': flop_bwd / (bwd_ms * 1e-3) / 1e12,
-                                  'fwd_tflops': flop_fwd / (fwd_ms * 1e-3) / 1e12,
-                                  'peak_tflops': fp32_peak / 1e12,
-                                  'bwd_frac': flop_bwd / (bwd_ms * 1e-3) / fp32_peak,
-                                  'fwd_frac': flop_fwd / (fwd_ms * 1e-3) / fp32_peak}},
+                         'fwd': {'achieved': fwd_bytes / (fwd_ms * 1e-3) / 1e9, 'algorithmic_bytes_per_launch': fwd_bytes,
+                                 'traffic': kf.get('dram_bytes')},
+                         'pipes_ncu': {'source': nm.get('_file'), 'note': 'counters of the committed ncu --set full capture of this '
+                                       'bench command (python bench.py --profile); not re-measured in this run',
+                                       'bwd': {k: kb.get(k) for k in ('fma_pipe_pct', 'xu_pipe_pct', 'issue_active_pct',
+                                                                      'registers', 'duration_us', 'warps_per_sm')},
+                                       'fwd': {k: kf.get(k) for k in ('fma_pipe_pct', 'xu_pipe_pct', 'issue_active_pct',
+                                                                      'registers', 'duration_us', 'warps_per_sm')}}},
             'e2e': {'value': world * npx / (e2e_ms * 1e-3) / 1e6, 'unit': 'Mpix/s', 'ms_per_step': e2e_ms,
-                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': n_e2e},
-            'gpu_launches': 2 * args.steps,   # one lobe-split kernel for the forward, one for the backward
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': n_e2e,
+                    'h2d_GBs_per_rank': h2d / (e2e_ms * 1e-3) / 1e9},
+            'gpu_launches': int(launches),   # irb_launch_count() delta over the timed region (this rank)
+            'gpu_launches_per_step': launches / args.steps,
             'clocks': clk,
+            'extras': extras,
         }
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = cpu_baseline(rows=args.cpu_baseline_rows)
         elif world > 1:
-            line['cpu_baseline'] = {'value': None, 'unit': 'Mpix/s', 'cores': os.cpu_count(), 'kind': 'port',
+            line['cpu_baseline'] = {'value': None, 'unit': 'Mpix/s', 'cores': os.cpu_count(), 'kind': 'reference',
                                     'sample': 'reported at N=1 only'}
         print(json.dumps(line))
     if world > 1:

@@ -268,6 +268,114 @@ def run_torchcuda(dev, iters):
             'Mpix_s': B * R * C / ms / 1e3}
 
 
+def run_reference_torch_cuda(dev, iters=3, B=2):
+    """BASELINE config 2's comparator: the UNMODIFIED reference render layer (baseline/_ref/models.py, isCuda=True) as a
+    PyTorch op graph on the SAME GPU -- output2env.output2env + renderingLayer.forwardEnv + autograd backward, all six
+    input gradients, 240x320, 12 SG.  Batch B (the reference materialises ~5 GB of temporaries per image)."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        return {'unavailable': 'baseline/_ref not present'}
+    ref = ref_loader.load('models')
+    R, C, K = 240, 320, 12
+    torch.cuda.set_device(dev)
+    alb, n, rg, ax, lam, wt = rand_inputs(B, R, C, R, C, K, dev, 1239)
+    g1 = torch.rand(B, 3, R, C, device=dev)
+    rl = ref.renderingLayer(imWidth=C, imHeight=R, isCuda=True)
+    o2e = ref.output2env(K, isCuda=True)
+
+    def step():
+        leaves = [t.detach().requires_grad_(True) for t in (alb, n, rg, ax, lam, wt)]
+        env, _, _, _ = o2e.output2env(leaves[3], leaves[4], leaves[5])
+        d, s = rl.forwardEnv(leaves[0], leaves[1], leaves[2], env)
+        torch.autograd.backward([d, s], [g1, g1])
+    ms = timed(step, iters, warm=1)
+    peak_gb = torch.cuda.max_memory_allocated(dev) / 2**30
+    torch.cuda.empty_cache()
+    return {'what': 'reference models.py (isCuda=True) torch-CUDA op graph on this GPU, %dx240x320, 12 SG, fwd+bwd all grads' % B,
+            'fwd_bwd_ms': ms, 'Mpix_s': B * R * C / ms / 1e3, 'peak_mem_GiB': peak_gb}
+
+
+def run_bilateral_mode0(BL, dev, iters=5):
+    """config 4 headline: BilateralFunction fwd+bwd, 8x480x640, mode 0 (3 channels)."""
+    import ctypes as C
+    from inverserenderingofindoorscene_b200 import _lib
+    from oracle import bilateral_oracle as bo  # synthetic guide generator only (test infrastructure)
+    B, H, W, ch = 8, 480, 640, 3
+    guide = torch.from_numpy(bo.synth_guide(B, H, W, blur_sigma=8.0, seed=1238)).to(dev)
+    sig, bsp = BL._PRESETS[0]
+    gp = torch.tensor([float(x) for x in sig], device=dev)
+    bp = torch.tensor([float(x) for x in bsp], device=dev)
+    g = torch.Generator(device=dev).manual_seed(5)
+    pred = torch.rand(B, ch, H, W, device=dev, generator=g)
+    conf = 0.05 + 0.95 * torch.rand(B, 1, H, W, device=dev, generator=g)
+    gout = torch.randn(B, ch, H, W, device=dev, generator=g)
+    holder = {}
+
+    def fwd():
+        p = pred.detach().requires_grad_(True)
+        c = conf.detach().requires_grad_(True)
+        o, _ = BL.BilateralFunction.apply(guide, p, c, gp, bp)
+        holder['x'] = (o, p, c)
+
+    def fwdbwd():
+        fwd()
+        o, p, c = holder['x']
+        torch.autograd.grad(o, [p, c], gout)
+    lib = _lib.lib()
+    l0 = lib.irb_launch_count()
+    fwdbwd()
+    launches = lib.irb_launch_count() - l0
+    f = timed(fwd, iters)
+    fb = timed(fwdbwd, iters)
+    # vertex / link counts of the grids (one extra build with the host read-back of V; E from the neighbour table)
+    nb = lib.irb_bg_workspace_bytes(B, H, W, ch)
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+    nv = (C.c_int * B)()
+    _lib.check(lib.irb_bg_build(_lib.ptr(guide), 255.0, B, H, W, float(sig[0]), float(sig[1]), float(sig[2]), _lib.ptr(ws), nb, nv,
+                                _lib.stream_ptr(dev)), 'irb_bg_build')
+    V = [int(x) for x in nv]
+    P = H * W
+    # streaming model of SURVEY 8d with THIS build's storage (fp64 vectors): per PCG iteration and vertex-channel
+    # 43 B (p-update) + 115 B (mat-vec) + 56 B (x/r update); 12 iterations forward + 12 adjoint; + compulsory pixel traffic
+    vsum = float(sum(V))
+    model_bytes = 2 * 12 * ch * vsum * (43 + 115 + 56) + B * P * 100.0
+    return {'what': 'BilateralFunction fwd+bwd, 8x480x640, mode 0 (3 ch, sigma 8/2/7, lam 200, 12 PCG iterations)',
+            'fwd_ms': f, 'fwd_bwd_ms': fb, 'Mpix_s_fwd_bwd': B * P / fb / 1e3, 'launches_fwd_bwd': int(launches),
+            'V_per_image': V, 'V_over_P': vsum / (B * P),
+            'streaming_model_GB': model_bytes / 1e9, 'streaming_model_GBs': model_bytes / (fb * 1e-3) / 1e9,
+            'hbm_frac_of_model': model_bytes / (fb * 1e-3) / 1e9 / peak_hbm()}
+
+
+def extras_for_bench(models, sharding, dev, rank, world, timed_ranks, make_render_step):
+    """secondary BASELINE configs for the bench line (`extras`): device-timed, max over ranks, a handful of steps each"""
+    from inverserenderingofindoorscene_b200 import BilateralLayer as BL
+    out = {}
+    # config 5: 480x640, 24 SG, 4 images per GPU (B = 32 over 8 GPUs), reference call pattern + loss all-reduce
+    step5 = make_render_step(models, sharding, dev, 4, 480, 640, 480, 640, 24, 1300 + rank)
+    ms5 = timed_ranks(step5, 5, 3, dev, world)
+    out['config5'] = {'what': 'config 5: 480x640, 24 SG, 4 images per GPU (global batch %d), fwd+bwd all grads + loss all-reduce'
+                              % (4 * world), 'ms_per_step': ms5, 'Mpix_s': world * 4 * 480 * 640 / ms5 / 1e3}
+    del step5
+    # config 3 geometry (trainLight: maps 240x320 pooled to a 120x160 grid, SG grads only): render-loss block, strong
+    # (global batch 16) and weak (16 per GPU)
+    for name, b in (('config3_strong', max(1, 16 // world)), ('config3_weak', 16)):
+        if world == 1 and name == 'config3_weak':
+            continue
+        st = make_render_step(models, sharding, dev, b, 240, 320, 120, 160, 12, 1400 + rank, all_grads=False)
+        ms = timed_ranks(st, 10, 3, dev, world)
+        out[name] = {'what': 'config 3 geometry: maps 240x320 -> grid 120x160, 12 SG, %d images per GPU (global batch %d), '
+                             'render-loss step (output2env -> forwardEnv -> render loss -> all-reduce -> backward to the SG '
+                             'parameters); the LightNet CNNs are out of scope' % (b, b * world),
+                     'ms_per_step': ms, 'images_per_s': b * world / ms * 1e3}
+        del st
+    torch.cuda.empty_cache()
+    if world == 1:
+        out['config4_bilateral'] = run_bilateral_mode0(BL, dev)
+        torch.cuda.empty_cache()
+        out['reference_torch_cuda'] = run_reference_torch_cuda(dev)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--which', default='trainlight,unfused,bilateral,k24,torchcuda')

@@ -39,6 +39,9 @@ extern "C" {
 
 int irb_abi_version(void);
 const char* irb_last_error(void);
+/* number of CUDA kernels this library has launched in this process so far (all threads); bench.py reports the
+ * difference over its timed region as `gpu_launches`. */
+long long irb_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------
  * SG lobes -> hemisphere env-map.  Replaces models.output2env.fromSGtoIm (models.py:371-389)
@@ -112,6 +115,21 @@ int irb_avgpool_bwd(const float* g_out, float* g_in, int N, int H, int W, int R,
 int irb_lsregress_diffspec(const float* diff, const float* spec, const float* im, const float* diff_orig,
                            const float* spec_orig, float* out_diff, float* out_spec, float* coef, double* stats,
                            int B, long long n_per_sample, void* stream);
+
+/* Fused render loss of the light branch.  Replaces, with three launches and no host sync,
+ *   dS, sS = models.LSregressDiffSpec(diff.detach(), spec.detach(), im, diff, spec)      (wrapperBRDFLight.py:197-201)
+ *   rend   = clamp(dS + sS, 0, 1)                                                          (wrapperBRDFLight.py:203)
+ *   num    = sum((rend - im)^2 * seg),  cnt = sum(seg)     (wrapperBRDFLight.py:192,205-207: renderErr = num/cnt/3,
+ *            the reference fetches cnt = pixelNum to the host with .item(); here it stays on the device)
+ * diff / spec / im [B,ch,n_pix], seg [B,n_pix] (broadcast over channels).  Outputs: rendered [B,ch,n_pix] (NULL = skip),
+ * gbase [B,ch,n_pix] = d num / d(dS+sS) (NULL = skip), coef [B,2] = (cI cD, cI cS), terms[2] fp64 = {num, cnt} (device),
+ * stats = scratch of 8*B doubles.
+ * irb_render_loss_bwd: g_diff = *g_num * coef[b,0] * gbase, g_spec = *g_num * coef[b,1] * gbase (g_num = device scalar
+ * dL/dnum, NULL = 1; the coefficients are graph constants as in models.py:58,76). */
+int irb_render_loss_fwd(const float* diff, const float* spec, const float* im, const float* seg, float* rendered, float* gbase,
+                        float* coef, double* stats, double* terms, int B, int ch, long long n_pix, void* stream);
+int irb_render_loss_bwd(const float* gbase, const float* coef, const float* g_num, float* g_diff, float* g_spec, int B, int ch,
+                        long long n_pix, void* stream);
 
 /* models.LSregress (models.py:7-21): coef[b] = clamp(sum(pred*gt)/clamp(sum(pred^2),1e-5), 1e-3, 1e3) per sample,
  * out = origin * coef (coef is a constant of the autograd graph, models.py:13 .detach()).  pred / gt / origin / out

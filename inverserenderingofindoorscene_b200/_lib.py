@@ -17,6 +17,7 @@ _D = C.c_double
 SIGNATURES = {
     'irb_abi_version': [],
     'irb_last_error': [],
+    'irb_launch_count': [],
     'irb_sg_to_env_fwd': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     'irb_sg_to_env_bwd': [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     'irb_render_env_fwd': [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
@@ -26,6 +27,8 @@ SIGNATURES = {
     'irb_avgpool_fwd': [_P, _P, _I, _I, _I, _I, _I, _P],
     'irb_avgpool_bwd': [_P, _P, _I, _I, _I, _I, _I, _P],
     'irb_lsregress_diffspec': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, C.c_longlong, _P],
+    'irb_render_loss_fwd': [_P] * 9 + [_I, _I, C.c_longlong, _P],
+    'irb_render_loss_bwd': [_P] * 5 + [_I, _I, C.c_longlong, _P],
     'irb_lsregress': [_P, _P, _P, _P, _P, _P, _I, C.c_longlong, _P],
     'irb_sg_reconst_fwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     'irb_sg_reconst_bwd': [_P] * 10 + [_I, _I, _I, _I, _I, _I, _I, _F, _P],
@@ -36,7 +39,7 @@ SIGNATURES = {
     'irb_bg_solve_fwd': [_P, _P, _P, _I, _I, _I, _I, _D, _D, _D, _I, _P, _P, _P],
     'irb_bg_solve_bwd': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _D, _D, _D, _I, _P, _P, _P],
 }
-_RESTYPE = {'irb_last_error': C.c_char_p, 'irb_bg_workspace_bytes': C.c_size_t}
+_RESTYPE = {'irb_last_error': C.c_char_p, 'irb_launch_count': C.c_longlong, 'irb_bg_workspace_bytes': C.c_size_t}
 
 _lib = None
 

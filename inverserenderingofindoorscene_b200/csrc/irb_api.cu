@@ -1,5 +1,6 @@
 // irb_api.cu -- error state, ABI version and the hemisphere direction table.
 #include <math.h>
+#include <atomic>
 #include <string.h>
 
 #include "irb_common.cuh"
@@ -7,6 +8,9 @@
 namespace irb {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -42,4 +46,5 @@ bool make_env_tab(EnvTab& tab, int envH, int envW) {
 extern "C" {
 int irb_abi_version(void) { return IRB_ABI_VERSION; }
 const char* irb_last_error(void) { return irb::g_err; }
+long long irb_launch_count(void) { return irb::g_launches.load(std::memory_order_relaxed); }
 }

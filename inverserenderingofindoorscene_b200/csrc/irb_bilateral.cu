@@ -651,7 +651,7 @@ static int run_pcg(void* ws, const BgLayout& L, SolveArgs a, int maxiter, cudaSt
             default: bg_xr_kernel<4><<<grid, 256, 0, st>>>(ws, L, a, it); break;
         }
     }
-    return check_launch("bilateral pcg");
+    return check_launch("bilateral pcg", 2 + 3 * maxiter);
 }
 
 }  // namespace irb
@@ -705,7 +705,7 @@ extern "C" int irb_bg_build(const float* guide, float guide_scale, int B, int H,
     bg_nbr_kernel<<<grid, 256, 0, st>>>(ws, L);
     for (int i = 0; i < 10; ++i) bg_bisto_iter_kernel<<<grid, 256, 0, st>>>(ws, L, i & 1);
     bg_bisto_final_kernel<<<grid, 256, 0, st>>>(ws, L, 0);  // after 10 iterations n is back in n0
-    if (int rc = check_launch("bg_build")) return rc;
+    if (int rc = check_launch("bg_build", 1 + 3 * npass + 2 + 1 + 11)) return rc;
     if (nverts_out) {
         cudaError_t e = cudaMemcpyAsync(nverts_out, at<int>(ws, L.hdr), sizeof(int) * B, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);

@@ -13,7 +13,10 @@ void set_error(const char* fmt, ...);
 // hemisphere table (models.py:353-362, 437-448); returns false if unsupported
 bool make_env_tab(EnvTab& tab, int envH, int envW);
 
-inline int check_launch(const char* what) {
+// every kernel launch of the library is counted (irb_launch_count): n = launches issued since the last check
+void count_launches(int n);
+inline int check_launch(const char* what, int n = 1) {
+    count_launches(n);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("%s: %s", what, cudaGetErrorString(e));

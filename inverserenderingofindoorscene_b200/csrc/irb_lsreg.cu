@@ -111,7 +111,94 @@ extern "C" int irb_lsregress_diffspec(const float* diff, const float* spec, cons
     lsreg_stats1_kernel<<<grid, 256, 0, st>>>(diff, spec, im, stats, n);
     lsreg_stats2_kernel<<<grid, 256, 0, st>>>(diff_orig, spec_orig, im, stats, n);  // models.py:66-72: on the scaled *Orig tensors
     lsreg_apply_kernel<<<grid, 256, 0, st>>>(diff_orig, spec_orig, stats, out_diff, out_spec, coef, n);
-    return check_launch("lsregress_diffspec");
+    return check_launch("lsregress_diffspec", 3);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused render loss (wrapperBRDFLight.py:197-207): LSregressDiffSpec -> clamp(dS + sS, 0, 1) -> masked L2
+// against the photo, its numerator / pixel count kept on the device (the reference's pixelNum is a host .item()), and the
+// backward seed.  Forward = stats1 + stats2 (above) + render_loss_kernel; backward = one elementwise kernel.
+//   x = kd d + ks s (kd = cI cD, ks = cI cS), rend = clamp(x, 0, 1), num += (rend - im)^2 seg, cnt += seg (once per pixel),
+//   gbase = d num / d x = 2 (rend - im) seg [0 <= x <= 1]   (torch.clamp's backward passes the gradient on the closed interval)
+// ---------------------------------------------------------------------------------------------
+namespace irb {
+
+__global__ void render_loss_kernel(const float* __restrict__ d, const float* __restrict__ s, const float* __restrict__ im,
+                                   const float* __restrict__ seg, const double* __restrict__ stats, float* __restrict__ rendered,
+                                   float* __restrict__ gbase, float* __restrict__ coef, double* __restrict__ terms, size_t n,
+                                   size_t npix) {
+    const int b = blockIdx.y;
+    float cD, cS;
+    const double* st = stats + (size_t)b * 8;
+    ls_coefs(st, (double)n, cD, cS);
+    const float cI = (float)fmin(fmax(st[5] / fmax(st[6], 1e-5), 0.001), 1000.0);
+    const float kd = cI * cD, ks = cI * cS;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        coef[2 * b] = kd;
+        coef[2 * b + 1] = ks;
+    }
+    const float* sg = seg + (size_t)b * npix;
+    float num = 0.f, cnt = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t o = (size_t)b * n + i;
+        const float m = sg[i % npix];
+        const float x = kd * d[o] + ks * s[o];
+        const float r = __saturatef(x);
+        const float e = r - im[o];
+        num += e * e * m;
+        if (i < npix) cnt += m;
+        if (rendered) rendered[o] = r;
+        if (gbase) gbase[o] = (x >= 0.f && x <= 1.f) ? 2.f * e * m : 0.f;
+    }
+    block_sum_atomic(num, terms);
+    block_sum_atomic(cnt, terms + 1);
+}
+
+__global__ void render_loss_seed_kernel(const float* __restrict__ gbase, const float* __restrict__ coef, const float* __restrict__ g_num,
+                                        float* __restrict__ g_diff, float* __restrict__ g_spec, size_t n) {
+    const int b = blockIdx.y;
+    const float gn = g_num ? *g_num : 1.f;
+    const float kd = gn * coef[2 * b], ks = gn * coef[2 * b + 1];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t o = (size_t)b * n + i;
+        const float g = gbase[o];
+        if (g_diff) g_diff[o] = kd * g;
+        if (g_spec) g_spec[o] = ks * g;
+    }
+}
+
+}  // namespace irb
+
+extern "C" int irb_render_loss_fwd(const float* diff, const float* spec, const float* im, const float* seg, float* rendered,
+                                   float* gbase, float* coef, double* stats, double* terms, int B, int ch, long long n_pix,
+                                   void* stream) {
+    IRB_REQUIRE(diff && spec && im && seg && coef && stats && terms, "render_loss_fwd: null pointer");
+    IRB_REQUIRE(B > 0 && B <= 65535 && ch > 0 && n_pix > 0, "render_loss_fwd: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)n_pix * (size_t)ch;
+    cudaMemsetAsync(stats, 0, sizeof(double) * 8 * (size_t)B, st);
+    cudaMemsetAsync(terms, 0, sizeof(double) * 2, st);
+    unsigned gx = (unsigned)((n + 256 * 8 - 1) / (256 * 8));
+    if (gx < 1) gx = 1;
+    if (gx > 1024) gx = 1024;
+    const dim3 grid(gx, (unsigned)B);
+    lsreg_stats1_kernel<<<grid, 256, 0, st>>>(diff, spec, im, stats, n);
+    lsreg_stats2_kernel<<<grid, 256, 0, st>>>(diff, spec, im, stats, n);
+    render_loss_kernel<<<grid, 256, 0, st>>>(diff, spec, im, seg, stats, rendered, gbase, coef, terms, n, (size_t)n_pix);
+    return check_launch("render_loss_fwd", 3);
+}
+
+extern "C" int irb_render_loss_bwd(const float* gbase, const float* coef, const float* g_num, float* g_diff, float* g_spec, int B,
+                                   int ch, long long n_pix, void* stream) {
+    IRB_REQUIRE(gbase && coef, "render_loss_bwd: null pointer");
+    IRB_REQUIRE(B > 0 && B <= 65535 && ch > 0 && n_pix > 0, "render_loss_bwd: bad shape");
+    if (!g_diff && !g_spec) return 0;
+    const size_t n = (size_t)n_pix * (size_t)ch;
+    unsigned gx = (unsigned)((n + 256 * 8 - 1) / (256 * 8));
+    if (gx < 1) gx = 1;
+    if (gx > 1024) gx = 1024;
+    render_loss_seed_kernel<<<dim3(gx, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(gbase, coef, g_num, g_diff, g_spec, n);
+    return check_launch("render_loss_bwd");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -185,5 +272,5 @@ extern "C" int irb_lsregress(const float* pred, const float* gt, const float* or
     const dim3 grid(gx, (unsigned)B);
     irb::lsreg_pg_kernel<<<grid, 256, 0, st>>>(pred, gt, stats, n, vec);
     irb::lsreg_scale_kernel<<<grid, 256, 0, st>>>(origin, stats, out, coef, n, vec);
-    return irb::check_launch("lsregress");
+    return irb::check_launch("lsregress", 2);
 }

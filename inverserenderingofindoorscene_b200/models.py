@@ -19,8 +19,13 @@ import numpy as np
 import torch
 
 from . import _lib
+from ._lazy import LazyTensor
 
-__all__ = ['output2env', 'renderingLayer', 'LSregress', 'LSregressDiffSpec']
+__all__ = ['output2env', 'renderingLayer', 'LSregress', 'LSregressDiffSpec', 'renderLoss', 'renderLossTerms']
+
+
+# measurement hook: a list that receives ('render_sg_bwd', start_event, end_event) per fused backward launch (bench.py)
+_EVENT_SINK = None
 
 
 def _chk(t, name, ndim=None):
@@ -228,11 +233,18 @@ class _RenderSG(torch.autograd.Function):
         g_s = _c(g_s) if g_s is not None else torch.zeros(B, 3, R, C, device=dev)
         outs = [torch.empty_like(t) if need[i] else None
                 for i, t in enumerate((albedo, normal, rough, axis, lamb, weight))]
+        sink = _EVENT_SINK
         with torch.cuda.device(dev):
+            if sink is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             _lib.check(_lib.lib().irb_render_sg_bwd(
                 _lib.ptr(albedo), _lib.ptr(normal), _lib.ptr(rough), _lib.ptr(axis), _lib.ptr(lamb),
                 _lib.ptr(weight), _lib.ptr(view), _lib.ptr(g_d), _lib.ptr(g_s), *[_lib.ptr(o) for o in outs],
                 B, K, R, C, envH, envW, F0, warp, _lib.stream_ptr(dev)), 'irb_render_sg_bwd')
+            if sink is not None:
+                e1.record()
+                sink.append(('render_sg_bwd', e0, e1))
         return tuple(outs) + (None, None, None, None, None)
 
 
@@ -279,23 +291,48 @@ class output2env():
         if lamb.device != axis.device or weight.device != axis.device:
             raise ValueError('axis / lamb / weight must live on one device')
 
-    def fromSGtoIm(self, axis, lamb, weight):
-        """models.py:371-389: lamb / weight already warped.  Returns envmaps [B,3,R,C,envH,envW]."""
-        self._check(axis, lamb, weight)
-        env, _, _ = _SgToEnv.apply(axis, lamb, weight, self.envHeight, self.envWidth, False)
+    def _lazy_env(self, axis, lamb, weight, warp):
+        """The env-map as a LazyTensor: evaluated by ``irb_sg_to_env_fwd`` on first use, never if the only
+        consumer is ``renderingLayer.forwardEnv`` (which renders from the lobes, _lazy.py)."""
+        B, K, _, R, C = axis.shape
+        srcs = (axis, lamb, weight)
+        vers = tuple(t._version for t in srcs)
+        envH, envW = self.envHeight, self.envWidth
+
+        def thunk():
+            if tuple(t._version for t in srcs) != vers:
+                raise RuntimeError('axis / lamb / weight were modified in place after output2env() and before its '
+                                   'env-map was first used: the lazily evaluated env-map would not be the one the '
+                                   'reference computed. Call env.materialize() right after output2env() or avoid the '
+                                   'in-place edit.')
+            return _SgToEnv.apply(axis, lamb, weight, envH, envW, warp)[0]
+        env = LazyTensor(thunk, (B, 3, R, C, envH, envW), axis.dtype, axis.device,
+                         torch.is_grad_enabled() and any(t.requires_grad for t in srcs))
+        if self.SGNum <= self.MAX_FUSED_LOBES:
+            env._irb_sg = (axis, lamb, weight, envH, envW, bool(warp), vers)
         return env
+
+    def fromSGtoIm(self, axis, lamb, weight):
+        """models.py:371-389: lamb / weight already warped.  Returns envmaps [B,3,R,C,envH,envW] (lazily evaluated)."""
+        self._check(axis, lamb, weight)
+        return self._lazy_env(axis, lamb, weight, False)
 
     def output2env(self, axisOrig, lambOrig, weightOrig):
         """models.py:391-404.  Returns (envmaps, axis, lamb, weight) like the reference.
 
-        The returned env-map remembers the SG parameters it came from, so that
-        ``renderingLayer.forwardEnv`` can take the fused kernel (the env-map is then never re-read).
-        """
+        ``envmaps`` is a ``LazyTensor`` (_lazy.py): it is written by ``irb_sg_to_env_fwd`` the first time any torch
+        operation touches it (wrapperBRDFLight.py:179-188 does), and never when it only travels on to
+        ``renderingLayer.forwardEnv`` (testReal.py:407-411), which renders from the SG lobes it came from in the
+        fused kernel.  Gradients of both consumers meet in ``axisOrig / lambOrig / weightOrig``.
+        The warped ``lamb`` / ``weight`` (3rd / 4th result, read by no caller) are lazy in the same way, evaluated
+        with the reference's literal expression ``tan(pi/2 * (0.999 * x))``."""
         self._check(axisOrig, lambOrig, weightOrig)
-        env, lamb, weight = _SgToEnv.apply(axisOrig, lambOrig, weightOrig, self.envHeight, self.envWidth, True)
-        if self.SGNum <= self.MAX_FUSED_LOBES:
-            env._irb_sg = (axisOrig, lambOrig, weightOrig, self.envHeight, self.envWidth)
-        return env, axisOrig, lamb, weight
+        env = self._lazy_env(axisOrig, lambOrig, weightOrig, True)
+
+        def warped(x):
+            return LazyTensor(lambda: torch.tan(np.pi / 2 * (0.999 * x)), x.shape, x.dtype, x.device,
+                              torch.is_grad_enabled() and x.requires_grad)
+        return env, axisOrig, warped(lambOrig), warped(weightOrig)
 
     def reconstLoss(self, axisOrig, lambOrig, weightOrig, envmapsBatch, segEnvBatch, offset=1.0):
         """Scale-invariant log-L2 reconstruction error of the predicted SG lighting against ``envmapsBatch``
@@ -390,16 +427,28 @@ class renderingLayer():
 
     # -- reference API -------------------------------------------------------------------------
     def forwardEnv(self, diffusePred, normalPred, roughPred, envmap):
-        """models.py:461-522.  Returns (colorDiffuse, colorSpec), each [B,3,R,C]."""
-        _chk(envmap, 'envmap', 6)
+        """models.py:461-522.  Returns (colorDiffuse, colorSpec), each [B,3,R,C].
+
+        An env-map that came from ``output2env.output2env`` / ``fromSGtoIm`` of this package (a LazyTensor carrying its
+        SG lobes) is rendered by the FUSED kernel straight from the lobes -- provided nothing modified or observed
+        it in between (``LazyTensor.irb_untouched`` and the lobes' version counters); any other env tensor takes
+        ``irb_render_env_fwd/bwd`` on its values."""
+        if not isinstance(envmap, torch.Tensor):
+            raise ValueError('envmap must be a torch.Tensor')
+        if envmap.dim() != 6:
+            raise ValueError('envmap must have 6 dims (got shape %s)' % (tuple(envmap.shape),))
         B, three, R, C, envH, envW = envmap.shape
         if three != 3 or (envH, envW) != (self.envHeight, self.envWidth):
             raise ValueError('envmap must be [B,3,R,C,%d,%d] (got %s)' % (self.envHeight, self.envWidth,
                                                                             tuple(envmap.shape)))
         self._check_maps(diffusePred, normalPred, roughPred, R, C)
-        sg = getattr(envmap, '_irb_sg', None)
-        if sg is not None and sg[3] == envH and sg[4] == envW:
-            return self.forwardSG(diffusePred, normalPred, roughPred, sg[0], sg[1], sg[2])
+        if isinstance(envmap, LazyTensor):
+            sg = envmap._irb_sg
+            if (sg is not None and envmap.irb_untouched()
+                    and tuple(t._version for t in sg[:3]) == sg[6]):
+                return self.forwardSG(diffusePred, normalPred, roughPred, sg[0], sg[1], sg[2], warp=sg[5])
+            envmap = envmap.materialize()
+        _chk(envmap, 'envmap', 6)
         dev = envmap.device
         A = _pool(diffusePred, R, C)
         N = _pool(normalPred, R, C)
@@ -512,6 +561,76 @@ def LSregressDiffSpec(diff, spec, imOrig, diffOrig, specOrig):
             and diff.shape == spec.shape == imOrig.shape == diffOrig.shape == specOrig.shape):
         return _LSregressDiffSpecFused.apply(diff, spec, imOrig, diffOrig, specOrig)
     return _LSregressDiffSpec_torch(diff, spec, imOrig, diffOrig, specOrig)
+
+
+class _RenderLoss(torch.autograd.Function):
+    """irb_render_loss_fwd/bwd: LSregressDiffSpec + clamp + masked L2 numerator / count (wrapperBRDFLight.py:197-207)."""
+
+    @staticmethod
+    def forward(ctx, diff, spec, im, seg):
+        diff, spec, im, seg = _c(diff), _c(spec), _c(im), _c(seg)
+        B, ch = diff.shape[0], diff.shape[1]
+        npix = diff.numel() // (B * ch)
+        dev = diff.device
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        rendered = torch.empty_like(diff)
+        gbase = torch.empty_like(diff) if need else None
+        coef = torch.empty(B, 2, device=dev, dtype=torch.float32)
+        scratch = torch.empty(8 * B + 2, device=dev, dtype=torch.float64)
+        terms = scratch[8 * B:]
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().irb_render_loss_fwd(
+                _lib.ptr(diff), _lib.ptr(spec), _lib.ptr(im), _lib.ptr(seg), _lib.ptr(rendered), _lib.ptr(gbase),
+                _lib.ptr(coef), _lib.ptr(scratch), _lib.ptr(terms), B, ch, npix, _lib.stream_ptr(dev)), 'irb_render_loss_fwd')
+        ctx.save_for_backward(gbase, coef)
+        ctx.dims = (B, ch, npix)
+        t32 = terms.float()
+        num, cnt = t32[0], t32[1]
+        ctx.mark_non_differentiable(rendered, cnt, coef)
+        return rendered, num, cnt, coef
+
+    @staticmethod
+    def backward(ctx, g_rend, g_num, g_cnt, g_coef):
+        gbase, coef = ctx.saved_tensors
+        B, ch, npix = ctx.dims
+        if g_num is None or gbase is None:
+            return None, None, None, None
+        g_num = _c(g_num.detach().to(torch.float32))
+        gd = torch.empty_like(gbase) if ctx.needs_input_grad[0] else None
+        gs = torch.empty_like(gbase) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(gbase.device):
+            _lib.check(_lib.lib().irb_render_loss_bwd(_lib.ptr(gbase), _lib.ptr(coef), _lib.ptr(g_num), _lib.ptr(gd), _lib.ptr(gs),
+                                                      B, ch, npix, _lib.stream_ptr(gbase.device)), 'irb_render_loss_bwd')
+        return gd, gs, None, None
+
+
+def renderLossTerms(diffusePred, specularPred, imBatchSmall, segBatchSmall):
+    """The render-loss block of wrapperBRDFLight.py:197-207 in three launches and without the host sync on ``pixelNum``:
+    ``LSregressDiffSpec(diff.detach(), spec.detach(), im, diff, spec)`` -> ``clamp(dS + sS, 0, 1)`` -> masked L2.
+
+    Returns ``(renderedImPred, num, cnt, coef)``: ``num = sum((rendered - im)^2 * seg)`` (differentiable w.r.t.
+    ``diffusePred`` / ``specularPred``, the regression coefficients being graph constants as in models.py:58,76),
+    ``cnt = sum(seg)``, ``coef[B,2]`` the total diffuse / specular scales.  ``renderErr = num / max(cnt, 1e-5) / 3``;
+    a multi-GPU caller feeds ``num, cnt`` to ``sharding.sharded_losses`` so that ``cnt`` is the batch-GLOBAL count
+    (wrapperBRDFLight.py:192).  ``renderedImPred`` is returned for display and carries no gradient.
+    Extension over the reference API."""
+    for t, n in ((diffusePred, 'diffusePred'), (specularPred, 'specularPred'), (imBatchSmall, 'imBatchSmall')):
+        _chk(t, n, 4)
+    _chk(segBatchSmall, 'segBatchSmall')
+    if not (diffusePred.shape == specularPred.shape == imBatchSmall.shape):
+        raise ValueError('diffusePred / specularPred / imBatchSmall must have one shape')
+    B, ch, R, C = diffusePred.shape
+    if segBatchSmall.numel() != B * R * C:
+        raise ValueError('segBatchSmall must hold one value per pixel, [B,1,R,C] (got %s)' % (tuple(segBatchSmall.shape),))
+    if imBatchSmall.requires_grad or segBatchSmall.requires_grad:
+        raise ValueError('renderLoss differentiates w.r.t. diffusePred / specularPred only')
+    return _RenderLoss.apply(diffusePred, specularPred, imBatchSmall, segBatchSmall.reshape(B, 1, R, C))
+
+
+def renderLoss(diffusePred, specularPred, imBatchSmall, segBatchSmall):
+    """``(renderedImPred, renderErr)`` of wrapperBRDFLight.py:197-207 (single-process normalisation)."""
+    rendered, num, cnt, _ = renderLossTerms(diffusePred, specularPred, imBatchSmall, segBatchSmall)
+    return rendered, num / torch.clamp(cnt, min=1e-5) / 3.0
 
 
 def _LSregressDiffSpec_torch(diff, spec, imOrig, diffOrig, specOrig):

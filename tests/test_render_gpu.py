@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN, relerr
+from conftest import GOLDEN, RENDER_NAMES, check_parity, oracle_render_both, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -31,12 +31,14 @@ def _run(irb, z, fused):
     rl = irb.renderingLayer(imWidth=C, imHeight=R, fov=float(z['fov']), isCuda=True)
     o2e = irb.output2env(K, isCuda=True)
     env, ax, lw, ww = o2e.output2env(ins[3], ins[4], ins[5])
+    from inverserenderingofindoorscene_b200._lazy import LazyTensor
+    assert isinstance(env, LazyTensor) and env._irb_sg is not None and not env.irb_materialized
     if fused:
-        assert getattr(env, '_irb_sg', None) is not None
         d, s = rl.forwardEnv(ins[0], ins[1], ins[2], env)
+        assert not env.irb_materialized      # the fused kernel rendered from the lobes; the env-map was never written
     else:
-        env_plain = env * 1.0          # drops the SG provenance -> unfused kernels
-        assert getattr(env_plain, '_irb_sg', None) is None
+        env_plain = env * 1.0          # an ordinary tensor: materialises the env-map -> unfused kernels
+        assert not isinstance(env_plain, LazyTensor) and env.irb_materialized
         d, s = rl.forwardEnv(ins[0], ins[1], ins[2], env_plain)
     gD = torch.from_numpy(z['gD']).to(dev)
     gS = torch.from_numpy(z['gS']).to(dev)
@@ -68,22 +70,17 @@ def test_oracle_parity_medium(irb):
     from oracle import render_oracle as ro
     B, H, W, R, C, K = 2, 60, 80, 30, 40, 12
     ins64 = ro.synth_inputs(B, H, W, R, C, K, seed=4321, dtype=torch.float64)
-    for t in ins64:
-        t.requires_grad_(True)
     g = torch.Generator().manual_seed(7)
     gD = torch.rand(B, 3, R, C, generator=g)
     gS = torch.rand(B, 3, R, C, generator=g)
-    d64, s64 = ro.render_sg(*ins64)
-    g64 = torch.autograd.grad((d64 * gD.double()).sum() + (s64 * gS.double()).sum(), ins64)
+    ref64, ref32 = oracle_render_both(ins64, gD, gS)
     dev = torch.device('cuda')
     ins = [t.detach().float().to(dev).requires_grad_(True) for t in ins64]
     rl = irb.renderingLayer(imWidth=C, imHeight=R, isCuda=True)
     d, s = rl.forwardSG(*ins)
     gg = torch.autograd.grad([d, s], ins, [gD.to(dev), gS.to(dev)])
-    assert relerr(d.detach().cpu().numpy(), d64.detach().numpy()) <= 1e-4
-    assert relerr(s.detach().cpu().numpy(), s64.detach().numpy()) <= 1e-4
-    for a, b, name in zip(gg, g64, ('albedo', 'normal', 'rough', 'axis', 'lamb', 'weight')):
-        assert relerr(a.cpu().numpy(), b.numpy()) <= 2e-4, name
+    for t, r64, r32, name in zip([d, s] + list(gg), ref64, ref32, RENDER_NAMES):
+        check_parity(t.detach().cpu().numpy(), r64, r32, name)
 
 
 def test_edge_cases_vs_oracle(irb):
@@ -104,12 +101,11 @@ def test_edge_cases_vs_oracle(irb):
     wt[0, 3:6] = 0.0
     rg[0, 0, 1, :] = -1.0                                # rho = 0 -> alpha2 = 0
     rg[0, 0, 2, :] = 1.0
-    ins64 = [t.float().double().requires_grad_(True) for t in ins64]
+    ins64 = [t.float().double() for t in ins64]
     g = torch.Generator().manual_seed(8)
     gD = torch.rand(B, 3, R, C, generator=g)
     gS = torch.rand(B, 3, R, C, generator=g)
-    d64, s64 = ro.render_sg(*ins64)
-    g64 = torch.autograd.grad((d64 * gD.double()).sum() + (s64 * gS.double()).sum(), ins64)
+    ref64, ref32 = oracle_render_both(ins64, gD, gS)
     dev = torch.device('cuda')
     ins = [t.detach().float().to(dev).requires_grad_(True) for t in ins64]
     rl = irb.renderingLayer(imWidth=C, imHeight=R, isCuda=True)
@@ -117,10 +113,8 @@ def test_edge_cases_vs_oracle(irb):
     gg = torch.autograd.grad([d, s], ins, [gD.to(dev), gS.to(dev)])
     for t in (d, s) + tuple(gg):
         assert torch.isfinite(t).all()
-    assert relerr(d.detach().cpu().numpy(), d64.detach().numpy()) <= 1e-4
-    assert relerr(s.detach().cpu().numpy(), s64.detach().numpy()) <= 1e-4
-    for a, b, name in zip(gg, g64, ('albedo', 'normal', 'rough', 'axis', 'lamb', 'weight')):
-        assert relerr(a.cpu().numpy(), b.numpy()) <= 5e-4, name
+    for t, r64, r32, name in zip([d, s] + list(gg), ref64, ref32, RENDER_NAMES):
+        check_parity(t.detach().cpu().numpy(), r64, r32, name)
 
 
 def test_full_size_properties(irb):
@@ -249,12 +243,9 @@ def test_tma_ring_many_tiles_per_cta(irb, cap, monkeypatch):
     monkeypatch.delenv('IRB_TMA_MAX_CTAS')
     for a, b in zip(plain, tma):   # same math, differently scheduled instantiations: round-off level agreement
         assert relerr(a.cpu().numpy(), b.cpu().numpy()) <= 2e-5
-    for t in ins64:
-        t.requires_grad_(True)
-    d64, s64 = ro.render_sg(*ins64)
-    g64 = torch.autograd.grad((d64 * gD.cpu().double()).sum() + (s64 * gS.cpu().double()).sum(), ins64)
-    for a, b in zip(tma, [d64, s64] + list(g64)):
-        assert relerr(a.cpu().numpy(), b.detach().numpy()) <= 2e-4
+    ref64, ref32 = oracle_render_both(ins64, gD.cpu(), gS.cpu())
+    for a, r64, r32, name in zip(tma, ref64, ref32, RENDER_NAMES):
+        check_parity(a.cpu().numpy(), r64, r32, name)
 
 
 def test_trainlight_loss_step_vs_oracle(irb):
@@ -286,21 +277,34 @@ def test_trainlight_loss_step_vs_oracle(irb):
         rerr = ((rend - im) * (rend - im) * seg.expand_as(im)).sum() / pixelNum / 3.0
         return rerr, reconst
 
-    ins_o = [t.clone().requires_grad_(True) for t in ins64]
-    r64, c64 = run(lambda a, l, w: ro.output2env(a, l, w)[0], lambda a, n, r, e: ro.render_env(a, n, r, e), ro.ls_regress,
-                   ro.ls_regress_diff_spec, ins_o, im, seg, envgt, segenv)
-    (r64 + 10 * c64).backward()
+    def oracle(dt):
+        ins_o = [t.clone().to(dt).requires_grad_(True) for t in ins64]
+        r, c = run(lambda a, l, w: ro.output2env(a, l, w)[0], lambda a, n, rr, e: ro.render_env(a, n, rr, e), ro.ls_regress,
+                   ro.ls_regress_diff_spec, ins_o, im.to(dt), seg.to(dt), envgt.to(dt), segenv.to(dt))
+        (r + 10 * c).backward()
+        return float(r), float(c), ins_o
+    r64, c64, ins_o = oracle(torch.float64)
+    r32, c32, ins_o32 = oracle(torch.float32)
     dev = torch.device('cuda')
     ins_g = [t.detach().float().to(dev).requires_grad_(True) for t in ins64]
     rl = irb.renderingLayer(imWidth=C, imHeight=R, isCuda=True)
     o2e = irb.output2env(K, isCuda=True)
-    rg_, cg_ = run(lambda a, l, w: o2e.output2env(a, l, w)[0], rl.forwardEnv, irb.LSregress, irb.LSregressDiffSpec, ins_g,
+    envs = []
+
+    def o2e_call(a, l, w):
+        envs.append(o2e.output2env(a, l, w)[0])
+        return envs[-1]
+    rg_, cg_ = run(o2e_call, rl.forwardEnv, irb.LSregress, irb.LSregressDiffSpec, ins_g,
                    im.float().to(dev), seg.float().to(dev), envgt.float().to(dev), segenv.float().to(dev))
+    # the env-map was materialised exactly once (by the reconstruction term) and forwardEnv still took the fused
+    # kernel: both gradient paths (sg_to_env backward + fused render backward) meet in the SG parameters
+    from inverserenderingofindoorscene_b200._lazy import LazyTensor
+    assert isinstance(envs[0], LazyTensor) and envs[0].irb_materialized and envs[0].irb_untouched()
     (rg_ + 10 * cg_).backward()
-    assert abs(float(rg_) - float(r64)) <= 1e-4 * abs(float(r64))
-    assert abs(float(cg_) - float(c64)) <= 1e-4 * abs(float(c64))
+    assert abs(float(rg_) - r64) <= max(1e-4, 2 * abs(r32 - r64) / abs(r64)) * abs(r64)
+    assert abs(float(cg_) - c64) <= max(1e-4, 2 * abs(c32 - c64) / abs(c64)) * abs(c64)
     for i, name in ((1, 'normal'), (2, 'rough'), (3, 'axis'), (4, 'lamb'), (5, 'weight')):
-        assert relerr(ins_g[i].grad.cpu().numpy(), ins_o[i].grad.numpy()) <= 3e-4, name
+        check_parity(ins_g[i].grad.cpu().numpy(), ins_o[i].grad.numpy(), ins_o32[i].grad.numpy(), name)
     assert ins_g[0].grad is None     # albedo is detached in the trainLight step
 
 
@@ -313,21 +317,18 @@ def test_lobe_counts_group_kernels(irb, K):
     ins64 = ro.synth_inputs(B, R, C, R, C, K, seed=500 + K, dtype=torch.float64, hi=0.95)
     ins64[1][0, :, 0, 0] = torch.tensor([0.0, 0.0, 0.0])
     ins64[1][1, :, 3, 5] = torch.tensor([0.2, 0.1, 1.3])
-    ins64 = [t.float().double().requires_grad_(True) for t in ins64]
+    ins64 = [t.float().double() for t in ins64]
     g = torch.Generator().manual_seed(K)
     gD = torch.rand(B, 3, R, C, generator=g)
     gS = torch.rand(B, 3, R, C, generator=g)
-    d64, s64 = ro.render_sg(*ins64)
-    g64 = torch.autograd.grad((d64 * gD.double()).sum() + (s64 * gS.double()).sum(), ins64)
+    ref64, ref32 = oracle_render_both(ins64, gD, gS)
     dev = torch.device('cuda')
     ins = [t.detach().float().to(dev).requires_grad_(True) for t in ins64]
     rl = irb.renderingLayer(imWidth=C, imHeight=R, isCuda=True)
     d, s = rl.forwardSG(*ins)
     gg = torch.autograd.grad([d, s], ins, [gD.to(dev), gS.to(dev)])
-    assert relerr(d.detach().cpu().numpy(), d64.detach().numpy()) <= 1e-4
-    assert relerr(s.detach().cpu().numpy(), s64.detach().numpy()) <= 1e-4
-    for a, b, name in zip(gg, g64, ('albedo', 'normal', 'rough', 'axis', 'lamb', 'weight')):
-        assert relerr(a.cpu().numpy(), b.numpy()) <= 3e-4, name
+    for t, r64, r32, name in zip([d, s] + list(gg), ref64, ref32, RENDER_NAMES):
+        check_parity(t.detach().cpu().numpy(), r64, r32, name)
 
 
 @pytest.mark.parametrize('envH,envW', [(4, 8), (8, 8), (2, 16)])
@@ -336,10 +337,7 @@ def test_other_env_tables(irb, envH, envW):
     from oracle import render_oracle as ro
     B, R, C, K = 1, 6, 8, 12
     ins64 = ro.synth_inputs(B, R, C, R, C, K, seed=77, dtype=torch.float64, hi=0.9)
-    for t in ins64:
-        t.requires_grad_(True)
-    d64, s64 = ro.render_sg(*ins64, envHeight=envH, envWidth=envW)
-    g64 = torch.autograd.grad(d64.sum() + 2 * s64.sum(), ins64)
+    ref64, ref32 = oracle_render_both(ins64, None, None, loss=lambda d, s: d.sum() + 2 * s.sum(), envHeight=envH, envWidth=envW)
     dev = torch.device('cuda')
     rl = irb.renderingLayer(imWidth=C, imHeight=R, envWidth=envW, envHeight=envH, isCuda=True)
     o2e = irb.output2env(K, envWidth=envW, envHeight=envH, isCuda=True)
@@ -349,10 +347,8 @@ def test_other_env_tables(irb, envH, envW):
         assert tuple(env.shape) == (B, 3, R, C, envH, envW)
         d, s = rl.forwardEnv(ins[0], ins[1], ins[2], env if fused else env * 1.0)
         gg = torch.autograd.grad(d.sum() + 2 * s.sum(), ins)
-        assert relerr(d.detach().cpu().numpy(), d64.detach().numpy()) <= 1e-4
-        assert relerr(s.detach().cpu().numpy(), s64.detach().numpy()) <= 1e-4
-        for a, b in zip(gg, g64):
-            assert relerr(a.cpu().numpy(), b.numpy()) <= 3e-4
+        for t, r64, r32, name in zip([d, s] + list(gg), ref64, ref32, RENDER_NAMES):
+            check_parity(t.detach().cpu().numpy(), r64, r32, name)
 
 
 def test_noncontiguous_and_needs_grad_subsets(irb):
@@ -379,9 +375,10 @@ def test_noncontiguous_and_needs_grad_subsets(irb):
 
 
 def test_lsregress_diffspec_fused(irb):
-    """fused irb_lsregress_diffspec against the PyTorch expression of models.py:23-84 and the reference fixture,
-    including the diffuse-only fallback branch and the gradient w.r.t. diffOrig / specOrig"""
-    from inverserenderingofindoorscene_b200.models import _LSregressDiffSpec_torch
+    """fused irb_lsregress_diffspec against the reference fixture and against the oracle's ls_regress_diff_spec
+    (pinned to the reference's models.py:23-84 by tests/test_oracle_golden.py) in fp64, with the oracle's own fp32 run
+    setting the tolerance; includes the diffuse-only fallback branch and the gradient w.r.t. diffOrig / specOrig"""
+    from oracle import render_oracle as ro
     dev = torch.device('cuda')
     z = dict(np.load(os.path.join(GOLDEN, 'render_pool2_full.npz')))
     d = torch.from_numpy(z['ref64_diff']).float().to(dev)
@@ -398,15 +395,20 @@ def test_lsregress_diffspec_fused(irb):
         sO = s.clone().requires_grad_(True)
         a1, a2 = irb.LSregressDiffSpec(d, s, im, dO, sO)
         (a1.sum() + 2 * a2.sum()).backward()
-        dO2 = d.clone().requires_grad_(True)
-        sO2 = s.clone().requires_grad_(True)
-        b1, b2 = _LSregressDiffSpec_torch(d, s, im, dO2, sO2)
-        (b1.sum() + 2 * b2.sum()).backward()
-        assert relerr(a1.detach().cpu().numpy(), b1.detach().cpu().numpy()) <= 2e-5
-        if scale_spec > 0:
-            assert relerr(a2.detach().cpu().numpy(), b2.detach().cpu().numpy()) <= 2e-4
-        assert relerr(dO.grad.cpu().numpy(), dO2.grad.cpu().numpy()) <= 2e-5
-        assert relerr(sO.grad.cpu().numpy(), sO2.grad.cpu().numpy()) <= 2e-4
+        refs = []
+        for dt in (torch.float64, torch.float32):
+            dc, sc, ic = d.cpu().to(dt), s.cpu().to(dt), im.cpu().to(dt)
+            dO2 = dc.clone().requires_grad_(True)
+            sO2 = sc.clone().requires_grad_(True)
+            b1, b2 = ro.ls_regress_diff_spec(dc, sc, ic, dO2, sO2)
+            (b1.sum() + 2 * b2.sum()).backward()
+            refs.append([b1.detach().numpy(), b2.detach().numpy(), dO2.grad.numpy(), sO2.grad.numpy()])
+        ours = [a1.detach(), a2.detach(), dO.grad, sO.grad]
+        for o, r64, r32, name in zip(ours, refs[0], refs[1], ('diff', 'spec', 'g_diffOrig', 'g_specOrig')):
+            if np.abs(r64).max() == 0:
+                assert float(o.abs().max()) == 0, name
+            else:
+                check_parity(o.cpu().numpy(), r64, r32, name)
 
 
 def test_lsregress_fused(irb):
