@@ -33,6 +33,16 @@ _OBSERVER_NAMES = {'register_hook', 'retain_grad', 'register_post_accumulate_gra
 _OBSERVER_FUNCS = {_T.grad.__get__, _T.grad.__set__, _T.requires_grad.__set__, _T.grad_fn.__get__, _T.retains_grad.__get__}
 
 
+def _wrapper_grad_error(grad):
+    raise RuntimeError('a gradient reached a LazyTensor wrapper directly: it was passed as an input of a custom '
+                       'torch.autograd.Function. Pass env.materialize() (or unlazy(env)) to such functions.')
+
+
+def unlazy(t):
+    """the real tensor behind a LazyTensor (materialising it), anything else unchanged"""
+    return t.materialize() if isinstance(t, LazyTensor) else t
+
+
 class LazyTensor(torch.Tensor):
     @staticmethod
     def __new__(cls, thunk, shape, dtype, device, requires_grad=False):
@@ -46,6 +56,12 @@ class LazyTensor(torch.Tensor):
         self._irb_observed = False
         self._irb_grad_mode = torch.is_grad_enabled()
         self._irb_sg = None   # set by models.output2env: (axis, lamb, weight, envH, envW, warp, versions)
+        if requires_grad:
+            # Every torch operation reaches the REAL tensor, so autograd never has a gradient for the wrapper itself --
+            # unless a custom autograd.Function took the wrapper as a direct input (Function.apply bypasses
+            # __torch_function__).  That gradient would be dropped silently; fail loudly instead.
+            with torch._C.DisableTorchFunctionSubclass():
+                torch.Tensor.register_hook(self, _wrapper_grad_error)
 
     # -- state -------------------------------------------------------------------------------
     def materialize(self):

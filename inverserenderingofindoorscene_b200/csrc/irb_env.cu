@@ -12,6 +12,7 @@
 
 #include "irb_driver_env.cuh"
 #include "irb_tma.cuh"
+#include "irb_launch.cuh"
 #include "irb_sg_env_group.cuh"
 
 namespace irb {
@@ -49,17 +50,12 @@ static int launch_sg_group(KernelT kernel, const SgEnvArgs& s, const EnvTab& tab
     const size_t tiles_per_img = (plane + tile - 1) / tile;
     const size_t total = tiles_per_img * (size_t)s.B;
     const size_t smem = 2 * (size_t)(7 * s.K) * tile * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-        set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", what, smem, cudaGetErrorString(e));
-        return (int)e;
+    int per_sm = 1;
+    if (int e = persistent_ctas_per_sm(kernel, 128, smem, &per_sm)) {
+        set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", what, smem, cudaGetErrorString((cudaError_t)e));
+        return e;
     }
-    int per_sm = 1, dev = 0, sms = 148;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, smem);
-    if (e != cudaSuccess || per_sm < 1) per_sm = 1;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    size_t grid = (size_t)sms * per_sm;
+    size_t grid = (size_t)cached_sms() * per_sm;
     if (grid > total) grid = total;
     if (const char* cap = getenv("IRB_TMA_MAX_CTAS")) {
         const long c = atol(cap);
@@ -70,8 +66,8 @@ static int launch_sg_group(KernelT kernel, const SgEnvArgs& s, const EnvTab& tab
     const char* tt = getenv("IRB_TMA_TENSOR");
     if (!(tt && tt[0] == '0') && plane < 0x7fffffffull) {
         const unsigned K = (unsigned)s.K, B = (unsigned)s.B, T = (unsigned)tile;
-        maps.on = make_tile_map(&maps.m[0], s.axis, plane, 3 * K, B, T) && make_tile_map(&maps.m[1], s.lamb, plane, K, B, T) &&
-                  make_tile_map(&maps.m[2], s.weight, plane, 3 * K, B, T);
+        maps.on = cached_tile_map(&maps.m[0], s.axis, plane, 3 * K, B, T) && cached_tile_map(&maps.m[1], s.lamb, plane, K, B, T) &&
+                  cached_tile_map(&maps.m[2], s.weight, plane, 3 * K, B, T);
     }
     kernel<<<(unsigned)grid, 128, smem, st>>>(s, tab, maps, (unsigned)total, (unsigned)tiles_per_img);
     return check_launch(what);

@@ -25,6 +25,7 @@
 #include "irb_common.cuh"
 #include "irb_driver.cuh"
 #include "irb_tma.cuh"
+#include "irb_launch.cuh"
 
 namespace irb {
 
@@ -143,13 +144,6 @@ struct Launch {
     int sms = 0;
 };
 
-static int device_sms() {
-    int dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return sms > 0 ? sms : 148;
-}
-
 // test knobs (environment): IRB_DISABLE_TMA=1 forces the plain kernels; IRB_TMA_MAX_CTAS=n caps the persistent
 // grid so that small test problems still walk many tiles per CTA (exercises the 2-stage ring)
 static bool tma_ok(const RenderSgArgs& a, bool bwd) {
@@ -175,15 +169,12 @@ static int launch_tma(KernelT kernel, const RenderSgArgs& a, const EnvTab& tab, 
         return IRB_E_UNSUPPORTED;
     }
     const size_t smem = 2 * (size_t)stage_planes(a.K, bwd) * tile * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-        set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", what, smem, cudaGetErrorString(e));
-        return (int)e;
-    }
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem);
-    if (e != cudaSuccess || per_sm < 1) per_sm = 1;
-    size_t grid = (size_t)device_sms() * per_sm;
+    if (int e = persistent_ctas_per_sm(kernel, kThreads, smem, &per_sm)) {
+        set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", what, smem, cudaGetErrorString((cudaError_t)e));
+        return e;
+    }
+    size_t grid = (size_t)cached_sms() * per_sm;
     if (grid > total) grid = total;
     if (const char* cap = getenv("IRB_TMA_MAX_CTAS")) {
         const long c = atol(cap);
@@ -210,23 +201,20 @@ static int launch_group(KernelT kernel, const RenderSgArgs& a, const EnvTab& tab
     const char* tt = getenv("IRB_TMA_TENSOR");
     if (!(tt && tt[0] == '0')) {
         const unsigned K = (unsigned)a.K, B = (unsigned)a.B, T = (unsigned)tile;
-        bool ok = make_tile_map(&maps.m[0], a.albedo, plane, 3, B, T) && make_tile_map(&maps.m[1], a.normal, plane, 3, B, T) &&
-                  make_tile_map(&maps.m[2], a.rough, plane, 1, B, T) && make_tile_map(&maps.m[3], a.view, plane, 3, 1, T) &&
-                  make_tile_map(&maps.m[4], a.axis, plane, 3 * K, B, T) && make_tile_map(&maps.m[5], a.lamb, plane, K, B, T) &&
-                  make_tile_map(&maps.m[6], a.weight, plane, 3 * K, B, T);
-        if (ok && bwd) ok = make_tile_map(&maps.m[7], a.g_diff, plane, 3, B, T) && make_tile_map(&maps.m[8], a.g_spec, plane, 3, B, T);
+        bool ok = cached_tile_map(&maps.m[0], a.albedo, plane, 3, B, T) && cached_tile_map(&maps.m[1], a.normal, plane, 3, B, T) &&
+                  cached_tile_map(&maps.m[2], a.rough, plane, 1, B, T) && cached_tile_map(&maps.m[3], a.view, plane, 3, 1, T) &&
+                  cached_tile_map(&maps.m[4], a.axis, plane, 3 * K, B, T) && cached_tile_map(&maps.m[5], a.lamb, plane, K, B, T) &&
+                  cached_tile_map(&maps.m[6], a.weight, plane, 3 * K, B, T);
+        if (ok && bwd) ok = cached_tile_map(&maps.m[7], a.g_diff, plane, 3, B, T) && cached_tile_map(&maps.m[8], a.g_spec, plane, 3, B, T);
         maps.on = ok ? 1 : 0;
     }
     const size_t smem = 2 * (size_t)stage_planes(a.K, bwd) * tile * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-        set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", what, smem, cudaGetErrorString(e));
-        return (int)e;
-    }
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem);
-    if (e != cudaSuccess || per_sm < 1) per_sm = 1;
-    size_t grid = (size_t)device_sms() * per_sm;
+    if (int e = persistent_ctas_per_sm(kernel, kThreads, smem, &per_sm)) {
+        set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", what, smem, cudaGetErrorString((cudaError_t)e));
+        return e;
+    }
+    size_t grid = (size_t)cached_sms() * per_sm;
     if (grid > total) grid = total;
     if (const char* cap = getenv("IRB_TMA_MAX_CTAS")) {
         const long c = atol(cap);

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lazy import LazyTensor
+from ._lazy import LazyTensor, unlazy
 
 __all__ = ['output2env', 'renderingLayer', 'LSregress', 'LSregressDiffSpec', 'renderLoss', 'renderLossTerms']
 
@@ -278,6 +278,8 @@ class output2env():
         self.ls.requires_grad = False
 
     def _check(self, axis, lamb, weight):
+        if any(isinstance(t, LazyTensor) for t in (axis, lamb, weight)):
+            raise ValueError('axis / lamb / weight must be ordinary tensors (got a LazyTensor; pass unlazy(t))')
         _chk(axis, 'axis', 5)
         _chk(lamb, 'lamb', 4)
         _chk(weight, 'weight', 4)
@@ -351,6 +353,8 @@ class output2env():
     def reconstTerms(self, axisOrig, lambOrig, weightOrig, envmapsBatch, segEnvBatch, offset=1.0):
         """(numerator, sum(seg), coef[B]) of ``reconstLoss`` -- the un-normalised pair a multi-GPU caller feeds to
         ``sharding.sharded_losses`` so that the loss is normalised by the batch-GLOBAL pixel count."""
+        axisOrig, lambOrig, weightOrig, envmapsBatch, segEnvBatch = [unlazy(t) for t in (axisOrig, lambOrig, weightOrig,
+                                                                                          envmapsBatch, segEnvBatch)]
         self._check(axisOrig, lambOrig, weightOrig)
         B, K, _, R, C = axisOrig.shape
         _chk(envmapsBatch, 'envmapsBatch', 6)
@@ -413,6 +417,8 @@ class renderingLayer():
         return v.reshape(3, self.imHeight, self.imWidth)
 
     def _check_maps(self, diffusePred, normalPred, roughPred, R, C):
+        if any(isinstance(t, LazyTensor) for t in (diffusePred, normalPred, roughPred)):
+            raise ValueError('diffusePred / normalPred / roughPred must be ordinary tensors (got a LazyTensor; pass unlazy(t))')
         _chk(diffusePred, 'diffusePred', 4)
         _chk(normalPred, 'normalPred', 4)
         _chk(roughPred, 'roughPred', 4)
@@ -508,6 +514,7 @@ def LSregress(pred, gt, origin):
 
     CUDA float32 tensors of one shape whose pred / gt carry no gradient (the reference's call pattern,
     wrapperBRDFLight.py:180-181) take the fused kernels; anything else the PyTorch expression."""
+    pred, gt, origin = unlazy(pred), unlazy(gt), unlazy(origin)   # autograd.Function.apply must see real tensors
     if (pred.is_cuda and pred.dtype == gt.dtype == origin.dtype == torch.float32 and pred.shape == gt.shape == origin.shape
             and pred.dim() >= 2 and not (pred.requires_grad or gt.requires_grad)):
         return _LSregressFused.apply(pred, gt, origin)
@@ -555,6 +562,7 @@ def LSregressDiffSpec(diff, spec, imOrig, diffOrig, specOrig):
     CUDA float32 inputs whose statistics tensors (diff, spec, imOrig) carry no gradient -- the reference's
     own call pattern, wrapperBRDFLight.py:197-201 -- take the fused kernel; anything else runs the
     PyTorch expression of the same formula."""
+    diff, spec, imOrig, diffOrig, specOrig = [unlazy(t) for t in (diff, spec, imOrig, diffOrig, specOrig)]
     if (diff.is_cuda and diff.dtype == torch.float32 and spec.dtype == torch.float32 and imOrig.dtype == torch.float32
             and diffOrig.dtype == torch.float32 and specOrig.dtype == torch.float32 and diff.dim() == 4
             and not (diff.requires_grad or spec.requires_grad or imOrig.requires_grad)
@@ -614,6 +622,8 @@ def renderLossTerms(diffusePred, specularPred, imBatchSmall, segBatchSmall):
     a multi-GPU caller feeds ``num, cnt`` to ``sharding.sharded_losses`` so that ``cnt`` is the batch-GLOBAL count
     (wrapperBRDFLight.py:192).  ``renderedImPred`` is returned for display and carries no gradient.
     Extension over the reference API."""
+    diffusePred, specularPred, imBatchSmall, segBatchSmall = [unlazy(t) for t in (diffusePred, specularPred, imBatchSmall,
+                                                                                  segBatchSmall)]
     for t, n in ((diffusePred, 'diffusePred'), (specularPred, 'specularPred'), (imBatchSmall, 'imBatchSmall')):
         _chk(t, n, 4)
     _chk(segBatchSmall, 'segBatchSmall')

@@ -41,26 +41,41 @@ def allreduce_loss_terms(terms, group=None):
     return red
 
 
-def _global_value_local_grad(local_num, global_num, scale):
-    # value = global_num*scale on every rank; gradient flows through the local numerator only
-    return (local_num - local_num.detach() + global_num) * scale
+class _GlobalValueLocalGrad(torch.autograd.Function):
+    """value = global_num * scale on every rank; gradient flows through the LOCAL numerator only (d/d local = scale)"""
+
+    @staticmethod
+    def forward(ctx, local_num, global_num, scale):
+        ctx.save_for_backward(scale)
+        return global_num * scale
+
+    @staticmethod
+    def backward(ctx, g):
+        scale, = ctx.saved_tensors
+        return g * scale, None, None
 
 
 def sharded_losses(render_num, render_cnt, reconst_num, reconst_cnt, envWidth=16, envHeight=8, group=None):
     """render_num = sum((rendered-im)^2*seg) over the LOCAL shard (differentiable), render_cnt = local
     sum(seg); same for the reconstruction pair.  Returns (renderErr, reconstErr) normalised exactly as
-    wrapperBRDFLight.py:183-207 does on the full batch."""
-    dev = render_num.device
-    z = torch.zeros((), device=dev, dtype=render_num.dtype)
-    terms = torch.stack([render_num.detach(), torch.as_tensor(render_cnt, device=dev, dtype=render_num.dtype),
-                         reconst_num.detach() if reconst_num is not None else z,
-                         torch.as_tensor(reconst_cnt if reconst_cnt is not None else 0.0, device=dev,
-                                         dtype=render_num.dtype)])
-    g = allreduce_loss_terms(terms, group)
-    cnt_r = torch.clamp(g[1], min=1e-5)
-    renderErr = _global_value_local_grad(render_num, g[0], 1.0 / cnt_r / 3.0)
+    wrapperBRDFLight.py:183-207 does on the full batch.  With one process (no initialised process group or world size
+    1) this is the plain single-process normalisation, no collective."""
+    dev, dt = render_num.device, render_num.dtype
+    multi = dist.is_initialized() and dist.get_world_size(group) > 1
+    with torch.no_grad():
+        parts = [render_num.detach().reshape(1), torch.as_tensor(render_cnt, device=dev, dtype=dt).reshape(1)]
+        if reconst_num is not None:
+            parts += [reconst_num.detach().reshape(1), torch.as_tensor(reconst_cnt, device=dev, dtype=dt).reshape(1)]
+        g = torch.cat(parts)
+        if multi:
+            if g.numel() < 4:
+                g = torch.cat([g, g.new_zeros(4 - g.numel())])   # always the same 4-float message
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+        cnt = torch.clamp(g[1::2], min=1e-5)
+        scale_r = 1.0 / (cnt[0] * 3.0)
+        scale_e = 1.0 / (cnt[1] * (3.0 * envWidth * envHeight)) if reconst_num is not None else None
+    renderErr = _GlobalValueLocalGrad.apply(render_num, g[0], scale_r)
     reconstErr = None
     if reconst_num is not None:
-        cnt_e = torch.clamp(g[3], min=1e-5)
-        reconstErr = _global_value_local_grad(reconst_num, g[2], 1.0 / cnt_e / 3.0 / envWidth / envHeight)
+        reconstErr = _GlobalValueLocalGrad.apply(reconst_num, g[2], scale_e)
     return renderErr, reconstErr

@@ -117,10 +117,10 @@ def test_render_loss_fused(irb):
         seg[:, :, :, :3] *= 0.5
         refs = []
         for dt in (torch.float64, torch.float32):
-            dd, ss = d.to(dt).requires_grad_(True), s.to(dt).requires_grad_(True)
+            dd, ss = d.to(dt).clone().requires_grad_(True), s.to(dt).clone().requires_grad_(True)
             err, rend, num, cnt = ro.render_loss(dd, ss, im.to(dt), seg.to(dt))
             err.backward()
-            refs.append((float(err), rend.detach().numpy(), float(num), float(cnt), dd.grad.numpy(), ss.grad.numpy()))
+            refs.append((float(err.detach()), rend.detach().numpy(), float(num.detach()), float(cnt), dd.grad.numpy(), ss.grad.numpy()))
         dg, sg = d.to(dev).requires_grad_(True), s.to(dev).requires_grad_(True)
         rend, err = irb.renderLoss(dg, sg, im.to(dev), seg.to(dev))
         err.backward()
