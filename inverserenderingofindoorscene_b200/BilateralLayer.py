@@ -31,9 +31,25 @@ def _chk(t, name, shape_tail=None):
         raise ValueError('%s must be float32 (got %s)' % (name, t.dtype))
 
 
+_PARAM_CACHE = {}
+
+
+def _host_values(t):
+    """the (few) values of a parameter tensor as Python floats.  The reference keeps sigma / lam / tol in device tensors
+    (BilateralLayer.py:145-149) and reads them back on every call (.cpu().numpy(), a device sync); here the read-back
+    happens once per (storage, version) and is cached -- no host sync on the steady-state path."""
+    key = (t.data_ptr(), t._version, str(t.device), t.numel())
+    v = _PARAM_CACHE.get(key)
+    if v is None:
+        if len(_PARAM_CACHE) > 256:
+            _PARAM_CACHE.clear()
+        v = _PARAM_CACHE[key] = tuple(float(x) for x in t.detach().cpu().tolist())
+    return v
+
+
 def _solver_params(grid_params_arr, bs_params_arr):
-    gp = [float(x) for x in grid_params_arr.detach().cpu().tolist()]
-    bp = [float(x) for x in bs_params_arr.detach().cpu().tolist()]
+    gp = _host_values(grid_params_arr)
+    bp = _host_values(bs_params_arr)
     maxiter = int(round(bp[3])) if CG_MAXITER_OVERRIDE is None else int(CG_MAXITER_OVERRIDE)
     return gp[0], gp[1], gp[2], bp[0], bp[1], bp[2], maxiter
 
@@ -55,6 +71,9 @@ class BilateralFunction(torch.autograd.Function):
         if tuple(image.shape) != (B, 3, H, W) or tuple(confidence.shape) != (B, 1, H, W):
             raise ValueError('image must be [B,3,H,W] and confidence [B,1,H,W] for pred %s (got %s, %s)'
                              % (tuple(pred.shape), tuple(image.shape), tuple(confidence.shape)))
+        if image.device != pred.device or confidence.device != pred.device:
+            raise ValueError('image / pred / confidence must live on one device (got %s, %s, %s)'
+                             % (image.device, pred.device, confidence.device))
         sl, sc, ss, lam, dmin, tol, maxiter = _solver_params(grid_params_arr, bs_params_arr)
         dev = pred.device
         image_c, pred_c, conf_c = image.contiguous(), pred.contiguous(), confidence.contiguous()

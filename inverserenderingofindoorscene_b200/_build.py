@@ -23,8 +23,9 @@ def sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith('.cu'))
 
 
-def _digest():
+def _digest(defines=()):
     h = hashlib.sha256()
+    h.update(' '.join(defines).encode())
     for f in sorted(os.listdir(CSRC)) + ['../../include/irb.h']:
         p = os.path.join(CSRC, f)
         if os.path.isfile(p):
@@ -34,9 +35,9 @@ def _digest():
     return h.hexdigest()
 
 
-def _compile(src):
-    obj = os.path.join(OBJ, src[:-3] + '.o')
-    cmd = [NVCC] + ARCH + FLAGS + ['-c', os.path.join(CSRC, src), '-o', obj]
+def _compile(src, objdir=OBJ, defines=()):
+    obj = os.path.join(objdir, src[:-3] + '.o')
+    cmd = [NVCC] + ARCH + FLAGS + ['-D' + d for d in defines] + ['-c', os.path.join(CSRC, src), '-o', obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(obj + '.log', 'w') as f:
@@ -46,15 +47,19 @@ def _compile(src):
     return obj
 
 
-def build(force=False, verbose=False):
-    os.makedirs(OBJ, exist_ok=True)
-    stamp = os.path.join(OBJ, 'digest.txt')
-    dig = _digest()
-    if (not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig):
-        return LIB
+def build(force=False, verbose=False, defines=(), variant=None):
+    """default: libirb_b200.so.  ``variant='x', defines=('IRB_FOO=0',)`` builds libirb_b200_x.so with extra -D flags for
+    A/B runs on the GPU box (select it with IRB_LIB=<path>, see _lib.py); variants are experiment artefacts, git-ignored."""
+    lib = LIB if variant is None else os.path.join(PKG, 'libirb_b200_%s.so' % variant)
+    objdir = OBJ if variant is None else os.path.join(OBJ, variant)
+    os.makedirs(objdir, exist_ok=True)
+    stamp = os.path.join(objdir, 'digest.txt')
+    dig = _digest(defines)
+    if (not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read() == dig):
+        return lib
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
-        objs = list(ex.map(_compile, sources()))
-    cmd = [NVCC] + ARCH + ['-shared', '-o', LIB] + objs
+        objs = list(ex.map(lambda src: _compile(src, objdir, defines), sources()))
+    cmd = [NVCC] + ARCH + ['-shared', '-o', lib] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n' + r.stdout + r.stderr)
@@ -63,7 +68,7 @@ def build(force=False, verbose=False):
     if verbose:
         for o in objs:
             print(open(o + '.log').read())
-    return LIB
+    return lib
 
 
 if __name__ == '__main__':

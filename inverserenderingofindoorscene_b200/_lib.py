@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, 'libirb_b200.so')
+# IRB_LIB selects another build of the same sources (A/B variants made by _build.build(variant=...)); default = the product
+LIB_PATH = os.environ.get('IRB_LIB') or os.path.join(PKG, 'libirb_b200.so')
 
 _P = C.c_void_p
 _I = C.c_int

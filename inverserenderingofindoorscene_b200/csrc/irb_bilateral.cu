@@ -13,6 +13,7 @@
 // x/r update + <r,z>, <r,r>),
 // all images and channels batched in each launch, scalars accumulated per (image, channel, iteration).
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "irb_common.cuh"
 
@@ -357,6 +358,7 @@ struct SolveArgs {
     double* x;           // [B,ch,P] solution (yhat buffer of the caller)
     double lam, dmin, tol;
     int adjoint;         // 0: b = S(x*w), y0 = b/max(Sw,1e-10) ; 1: b = S(g), y0 = b/S(1)
+    int b0;              // first image of the group this launch works on (grid.y = images in the group)
 };
 
 __device__ __forceinline__ double* scal_ptr(void* ws, const BgLayout& L, int b, int c, int it) {
@@ -394,7 +396,7 @@ __device__ __forceinline__ void block_atomic_add_n(double (&v)[N], double* const
 // splat (ordered segmented sums), system diagonal, flat initialisation (BilateralGrid.py:134-145 / 160-168)
 __global__ void bg_setup_kernel(void* ws, BgLayout L, SolveArgs a) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
+    const int b = blockIdx.y + a.b0;
     const size_t P = L.P;
     const int V = at<int>(ws, L.hdr)[b];
     const bool ok = t < (size_t)V;
@@ -447,7 +449,7 @@ __device__ __forceinline__ double bg_matvec(F y, const double* __restrict__ n, c
 // r0 = b - A x0 ; rho0 = <r0, M r0> ; rr0 = <r0, r0>
 __global__ void bg_r0_kernel(void* ws, BgLayout L, SolveArgs a) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
+    const int b = blockIdx.y + a.b0;
     const size_t P = L.P;
     const int V = at<int>(ws, L.hdr)[b];
     const bool ok = t < (size_t)V;
@@ -482,7 +484,7 @@ __device__ __forceinline__ bool bg_done(void* ws, const BgLayout& L, int b, int 
 template <int CH>
 __global__ void __launch_bounds__(256) bg_p_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
+    const int b = blockIdx.y + a.b0;
     const size_t P = L.P;
     if (t >= (size_t)at<int>(ws, L.hdr)[b]) return;
     bool done[CH];
@@ -515,7 +517,7 @@ __global__ void __launch_bounds__(256) bg_p_kernel(void* ws, BgLayout L, SolveAr
 // iteration `it`, step 2:  q = A p = lam (m p - n blur(n p)) + wsplat p ;  pq = <p,q>
 __global__ void bg_q_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
+    const int b = blockIdx.y + a.b0;
     const size_t P = L.P;
     const int V = at<int>(ws, L.hdr)[b];
     const bool ok = t < (size_t)V;
@@ -563,7 +565,7 @@ __global__ void bg_q_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
 template <int CH>
 __global__ void __launch_bounds__(256) bg_xr_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
+    const int b = blockIdx.y + a.b0;
     const size_t P = L.P;
     const int V = at<int>(ws, L.hdr)[b];
     const bool ok = t < (size_t)V;
@@ -630,28 +632,48 @@ __global__ void bg_grad_kernel(const void* ws, BgLayout L, const double* __restr
     if (g_conf) g_conf[(size_t)b * L.P + t] = (float)gc;
 }
 
+// Images are solved in GROUPS whose solver vectors fit the 126 MB L2 together (fp64: ~200 B per vertex, ~0.63 P vertices per
+// image at the reference's presets): every PCG iteration re-reads the same vectors, so a group that fits L2 streams them from
+// L2 instead of HBM (all 8 images of config 4 at once are 300 MB: every iteration went to HBM).  IRB_BG_GROUP overrides.
+static int pcg_group(const BgLayout& L) {
+    if (const char* g = getenv("IRB_BG_GROUP")) {
+        const int v = atoi(g);
+        if (v > 0) return v < L.B ? v : L.B;
+    }
+    const double per_image = 0.7 * (double)L.P * (64.0 * L.ch + 100.0);   // bytes touched per iteration and image (upper estimate)
+    int g = (int)(80e6 / per_image);
+    if (g < 1) g = 1;
+    return g < L.B ? g : L.B;
+}
+
 static int run_pcg(void* ws, const BgLayout& L, SolveArgs a, int maxiter, cudaStream_t st) {
     const unsigned gx = (unsigned)((L.P + 255) / 256);
-    const dim3 grid(gx, (unsigned)L.B);
     cudaMemsetAsync(at<double>(ws, L.scal), 0, 8 * (size_t)L.B * BG_MAX_CH * (BG_MAX_ITERS + 2) * 4, st);
-    bg_setup_kernel<<<grid, 256, 0, st>>>(ws, L, a);
-    bg_r0_kernel<<<grid, 256, 0, st>>>(ws, L, a);
-    for (int it = 0; it < maxiter; ++it) {
-        switch (L.ch) {
-            case 1: bg_p_kernel<1><<<grid, 256, 0, st>>>(ws, L, a, it); break;
-            case 2: bg_p_kernel<2><<<grid, 256, 0, st>>>(ws, L, a, it); break;
-            case 3: bg_p_kernel<3><<<grid, 256, 0, st>>>(ws, L, a, it); break;
-            default: bg_p_kernel<4><<<grid, 256, 0, st>>>(ws, L, a, it); break;
+    const int G = pcg_group(L);
+    int launches = 0;
+    for (int b0 = 0; b0 < L.B; b0 += G) {
+        const dim3 grid(gx, (unsigned)(L.B - b0 < G ? L.B - b0 : G));
+        a.b0 = b0;
+        bg_setup_kernel<<<grid, 256, 0, st>>>(ws, L, a);
+        bg_r0_kernel<<<grid, 256, 0, st>>>(ws, L, a);
+        for (int it = 0; it < maxiter; ++it) {
+            switch (L.ch) {
+                case 1: bg_p_kernel<1><<<grid, 256, 0, st>>>(ws, L, a, it); break;
+                case 2: bg_p_kernel<2><<<grid, 256, 0, st>>>(ws, L, a, it); break;
+                case 3: bg_p_kernel<3><<<grid, 256, 0, st>>>(ws, L, a, it); break;
+                default: bg_p_kernel<4><<<grid, 256, 0, st>>>(ws, L, a, it); break;
+            }
+            bg_q_kernel<<<grid, 256, 0, st>>>(ws, L, a, it);
+            switch (L.ch) {
+                case 1: bg_xr_kernel<1><<<grid, 256, 0, st>>>(ws, L, a, it); break;
+                case 2: bg_xr_kernel<2><<<grid, 256, 0, st>>>(ws, L, a, it); break;
+                case 3: bg_xr_kernel<3><<<grid, 256, 0, st>>>(ws, L, a, it); break;
+                default: bg_xr_kernel<4><<<grid, 256, 0, st>>>(ws, L, a, it); break;
+            }
         }
-        bg_q_kernel<<<grid, 256, 0, st>>>(ws, L, a, it);
-        switch (L.ch) {
-            case 1: bg_xr_kernel<1><<<grid, 256, 0, st>>>(ws, L, a, it); break;
-            case 2: bg_xr_kernel<2><<<grid, 256, 0, st>>>(ws, L, a, it); break;
-            case 3: bg_xr_kernel<3><<<grid, 256, 0, st>>>(ws, L, a, it); break;
-            default: bg_xr_kernel<4><<<grid, 256, 0, st>>>(ws, L, a, it); break;
-        }
+        launches += 2 + 3 * maxiter;
     }
-    return check_launch("bilateral pcg", 2 + 3 * maxiter);
+    return check_launch("bilateral pcg", launches);
 }
 
 }  // namespace irb
@@ -737,7 +759,7 @@ extern "C" int irb_bg_solve_fwd(void* ws, const float* pred, const float* conf, 
     IRB_REQUIRE(cg_maxiter >= 0 && cg_maxiter <= BG_MAX_ITERS, "bg_solve_fwd: cg_maxiter must be in [0,%d]", BG_MAX_ITERS);
     const BgLayout L = make_layout(B, H, W, ch);
     cudaStream_t st = (cudaStream_t)stream;
-    SolveArgs a{pred, conf, pred, yhat, lam, A_diag_min, cg_tol, 0};
+    SolveArgs a{pred, conf, pred, yhat, lam, A_diag_min, cg_tol, 0, 0};
     if (int rc = run_pcg(ws, L, a, cg_maxiter, st)) return rc;
     const dim3 grid((unsigned)((L.P + 255) / 256), (unsigned)B);
     bg_slice_kernel<<<grid, 256, 0, st>>>(ws, L, yhat, out);
@@ -753,7 +775,7 @@ extern "C" int irb_bg_solve_bwd(void* ws, const float* pred, const float* conf, 
     const BgLayout L = make_layout(B, H, W, ch);
     cudaStream_t st = (cudaStream_t)stream;
     double* gh = at<double>(ws, L.sol);
-    SolveArgs a{pred, conf, g_out, gh, lam, A_diag_min, cg_tol, 1};
+    SolveArgs a{pred, conf, g_out, gh, lam, A_diag_min, cg_tol, 1, 0};
     if (int rc = run_pcg(ws, L, a, cg_maxiter, st)) return rc;
     const dim3 grid((unsigned)((L.P + 255) / 256), (unsigned)B);
     bg_grad_kernel<<<grid, 256, 0, st>>>(ws, L, gh, yhat, pred, conf, g_pred, g_conf);

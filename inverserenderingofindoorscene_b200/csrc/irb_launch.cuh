@@ -41,26 +41,34 @@ template <typename KernelT> inline int persistent_ctas_per_sm(KernelT kernel, in
         }
     };
     static std::mutex mu;
-    static std::unordered_map<Key, int, Hash> cache;
+    static std::unordered_map<Key, int, Hash> cache;       // (kernel, smem, threads, device) -> resident CTAs per SM
+    static std::unordered_map<Key, size_t, Hash> attr;     // (kernel, device) -> largest dynamic smem size set so far
     int dev = 0;
     cudaGetDevice(&dev);
     const Key key{(const void*)kernel, smem, threads, dev};
+    const Key akey{(const void*)kernel, 0, 0, dev};
+    bool need_attr = true;
     {
         std::lock_guard<std::mutex> g(mu);
+        auto ia = attr.find(akey);
+        need_attr = (ia == attr.end()) || ia->second < smem;   // the attribute is a MAXIMUM: only ever raise it
         auto it = cache.find(key);
-        if (it != cache.end()) {
+        if (it != cache.end() && !need_attr) {
             *per_sm = it->second;
             return 0;
         }
     }
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    if (need_attr) {
+        const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
     int n = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem);
+    const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem);
     if (e != cudaSuccess || n < 1) n = 1;
     {
         std::lock_guard<std::mutex> g(mu);
         cache[key] = n;
+        if (need_attr) attr[akey] = smem;
     }
     *per_sm = n;
     return 0;

@@ -15,6 +15,13 @@
 // irb_driver.cuh (group_general_pixel below).
 #pragma once
 
+#ifndef IRB_BWD_ROTATE
+#define IRB_BWD_ROTATE 1
+#endif
+#ifndef IRB_FWD_PIPE
+#define IRB_FWD_PIPE 1
+#endif
+
 namespace irb {
 
 __device__ __forceinline__ void issue_tile_n(float* stage, uint64_t* bar, const RenderSgArgs& a, const TileMaps& maps, size_t tile,
@@ -107,12 +114,27 @@ __device__ __forceinline__ bool group_tile_fwd(const RenderSgArgs& a, const Rend
     for (int i = 0; i < kLPT / 2; ++i) U2[i] = V2[i] = pk(0.f, 0.f);
     // 2*TPP directions per iteration: this lane evaluates the BRDF chains of directions m+h and m+TPP+h packed in
     // the two halves of f32x2 registers
+#if IRB_FWD_PIPE
+    // software pipeline: the BRDF chain of the NEXT direction pair is issued in the same basic block as the lobe work of
+    // the current one (the chain is ~25 dependent steps deep; alone it leaves the FMA / XU pipes idle)
+    DirL2 dr;
+    dir_fwd_local2(dr, px, pl, pk(ts.lx[h], ts.lx[TPP + h]), pk(ts.ly[h], ts.ly[TPP + h]), pk(ts.lz[h], ts.lz[TPP + h]));
+    for (int m = 0; m < tab.D; m += 2 * TPP) {
+        float sp_lo, sp_hi;
+        upk(dr.spec, sp_lo, sp_hi);
+        {
+            const int mn = (m + 2 * TPP < tab.D) ? m + 2 * TPP : m;   // clamped on the last trip (result unused)
+            const int d0 = mn + h, d1 = mn + TPP + h;
+            dir_fwd_local2(dr, px, pl, pk(ts.lx[d0], ts.lx[d1]), pk(ts.ly[d0], ts.ly[d1]), pk(ts.lz[d0], ts.lz[d1]));
+        }
+#else
     for (int m = 0; m < tab.D; m += 2 * TPP) {
         const int d0 = m + h, d1 = m + TPP + h;
         DirL2 dr;
         dir_fwd_local2(dr, px, pl, pk(ts.lx[d0], ts.lx[d1]), pk(ts.ly[d0], ts.ly[d1]), pk(ts.lz[d0], ts.lz[d1]));
         float sp_lo, sp_hi;
         upk(dr.spec, sp_lo, sp_hi);
+#endif
         pk2 e[2 * TPP][kLPT / 2];
         pk2 w2[2 * TPP], ws2[2 * TPP];
 #pragma unroll
@@ -225,6 +247,70 @@ __device__ __forceinline__ bool group_tile_bwd(const RenderSgArgs& a, const Rend
         gradspk_zero<kLPT>(g2);
         PixelGradL2 gl2;
         pixel_gradl2_zero(gl2);
+#if IRB_BWD_ROTATE
+        // Rotated loop: the BRDF forward chain of the NEXT direction pair sits next to the BRDF backward chain of the
+        // current one (two independent, long, serially dependent chains in one basic block), so that the scheduler can
+        // interleave them -- with 2 warps per scheduler (255 registers) a lone chain leaves the FMA pipe idle for most of
+        // its ~25-deep dependency path (ncu r01: stall_wait 32 %).  The lobe temporaries are dead in that phase, so the
+        // second DirL2 does not raise the register peak.  Unrolled by two with ping-pong state (no register copies).
+        struct DirState {
+            DirL2 dr;
+            pk2 wx, wy, wz;
+        };
+        auto load_dirs = [&](DirState& st, int m) {
+            st.wx = pk(ts.lx[m + h], ts.lx[m + TPP + h]);
+            st.wy = pk(ts.ly[m + h], ts.ly[m + TPP + h]);
+            st.wz = pk(ts.lz[m + h], ts.lz[m + TPP + h]);
+            dir_fwd_local2(st.dr, px, pl, st.wx, st.wy, st.wz);
+        };
+        auto body = [&](int m, DirState& cur, DirState& nxt) {
+            float sp_lo, sp_hi;
+            upk(cur.dr.spec, sp_lo, sp_hi);
+            float part[2 * TPP];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {   // the two direction groups in turn: keeps only TPP*3 (arg, e) pairs live
+                pk2 arg[TPP][kLPT / 2], e[TPP][kLPT / 2];
+                float spec[TPP];
+#pragma unroll
+                for (int j = 0; j < TPP; ++j) {   // phase 1: arguments + exponentials
+                    const int d = m + half * TPP + j;
+                    const float wx = tab.lx[d], wy = tab.ly[d], wz = tab.lz[d];
+                    spec[j] = __shfl_sync(0xffffffffu, half ? sp_hi : sp_lo, lane_base + j);
+                    lobe_exps_pk<kLPT>(Lp, pk(wx, wx), pk(wy, wy), pk(wz, wz), arg[j], e[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < TPP; ++j) {   // phase 2: accumulations
+                    const int d = m + half * TPP + j;
+                    const float wx = tab.lx[d], wy = tab.ly[d], wz = tab.lz[d];
+                    part[half * TPP + j] =
+                        lobes_bwd_acc_pk<kLPT, PIX, LOBE>(g2, P2, Q2, arg[j], e[j], wx, wy, wz, tab.w[d] * wz, spec[j]);
+                }
+            }
+            // next pair (clamped on the last trip: recomputes the last pair, result unused)
+            load_dirs(nxt, (m + 2 * TPP < tab.D) ? m + 2 * TPP : m);
+            if (PIX) {
+                float pa[TPP], pb[TPP];
+#pragma unroll
+                for (int j = 0; j < TPP; ++j) {
+                    pa[j] = part[j];
+                    pb[j] = part[TPP + j];
+                }
+                const float s0 = grp_reduce_scatter<TPP>(pa, h), s1 = grp_reduce_scatter<TPP>(pb, h);
+                float z0, z1;
+                upk(cur.wz, z0, z1);
+                dir_bwd_local2(gl2, px, pl, cur.dr, cur.wx, cur.wy, cur.wz,
+                               pk(ts.w[m + h] * z0 * s0, ts.w[m + TPP + h] * z1 * s1));
+            }
+        };
+        DirState sa, sb;
+        load_dirs(sa, 0);
+        int m = 0;
+        for (; m + 4 * TPP <= tab.D; m += 4 * TPP) {
+            body(m, sa, sb);
+            body(m + 2 * TPP, sb, sa);
+        }
+        if (m < tab.D) body(m, sa, sb);
+#else
         for (int m = 0; m < tab.D; m += 2 * TPP) {
             const int d0 = m + h, d1 = m + TPP + h;
             const pk2 wxm = pk(ts.lx[d0], ts.lx[d1]), wym = pk(ts.ly[d0], ts.ly[d1]), wzm = pk(ts.lz[d0], ts.lz[d1]);
@@ -265,6 +351,7 @@ __device__ __forceinline__ bool group_tile_bwd(const RenderSgArgs& a, const Rend
                 dir_bwd_local2(gl2, px, pl, dr, wxm, wym, wzm, pk(ts.w[d0] * z0 * s0, ts.w[d1] * z1 * s1));
             }
         }
+#endif
         pixel_gradl2_fold(gl, gl2);
         gradspk_unpack<kLPT>(lg, g2);
     }
