@@ -16,6 +16,9 @@
  *   - return 0 on success, negative for argument errors (IRB_E_*), positive = cudaError_t;
  *     a thread-local message is available from irb_last_error();
  *   - gradient outputs may be NULL = "not needed"; they are OVERWRITTEN, not accumulated;
+ *   - env-map tensors (env, g_env, env_gt: [B,3,R,C,envH,envW]) must be 16-byte aligned (they are accessed as 16-byte
+ *     vectors; IRB_E_ARG otherwise) -- every torch allocation is; the other tensors have no alignment requirement (a
+ *     misaligned plane only disables the TMA-staged fast path);
  *   - B batch, K SG lobes, R x C render (env) grid, envH x envW hemisphere table
  *     (D = envH*envW <= IRB_MAX_DIRS), direction index d = i*envW + j.
  */
@@ -102,6 +105,12 @@ int irb_render_sg_bwd(const float* albedo, const float* normal, const float* rou
  * ------------------------------------------------------------------------------------- */
 int irb_avgpool_fwd(const float* in, float* out, int N, int H, int W, int R, int C, void* stream);
 int irb_avgpool_bwd(const float* g_out, float* g_in, int N, int H, int W, int R, int C, void* stream);
+/* the three maps forwardEnv pools (albedo, normal, rough: models.py:465-469) in ONE launch; tensor k has n_k = B*channels
+ * planes; a NULL in/out pair is skipped.  bwd: g* at R x C -> gi* at H x W. */
+int irb_avgpool3_fwd(const float* in0, const float* in1, const float* in2, float* out0, float* out1, float* out2, int n0, int n1,
+                     int n2, int H, int W, int R, int C, void* stream);
+int irb_avgpool3_bwd(const float* g0, const float* g1, const float* g2, float* gi0, float* gi1, float* gi2, int n0, int n1,
+                     int n2, int H, int W, int R, int C, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Fused scale-ambiguity regression.  Replaces models.LSregressDiffSpec (models.py:23-84) for the
@@ -189,6 +198,15 @@ int irb_bg_solve_fwd(void* ws, const float* pred, const float* conf, int B, int 
 int irb_bg_solve_bwd(void* ws, const float* pred, const float* conf, const float* g_out, const double* yhat,
                      int B, int ch, int H, int W, double lam, double A_diag_min, double cg_tol, int cg_maxiter,
                      float* g_pred, float* g_conf, void* stream);
+
+/* Primitive operators of a built grid (BilateralGrid.py:90-107), fp64 device buffers [B,ch,H*W] (vertex vectors use the
+ * first V entries of each plane, the rest is zero): op 0 = splat (S x, pixel -> vertex), 1 = slice (S^T y, vertex -> pixel),
+ * 2 = blur (2 dim y + sum of the five [1 0 1] neighbour sums, vertex -> vertex).  x and out must not alias. */
+int irb_bg_apply(const void* ws, int op, const double* x, double* out, int B, int ch, int H, int W, void* stream);
+/* the bistochastisation vectors n, m of BilateralGrid.bistochastize (BilateralGrid.py:109-120), device fp64 [B,H*W] */
+int irb_bg_bistochastization(const void* ws, double* n, double* m, int B, int H, int W, void* stream);
+/* per image: number of vertices V (device int[B]) and of directed neighbour links E (device uint64[B]) -- SURVEY 8d */
+int irb_bg_stats(const void* ws, int* nverts, unsigned long long* nlinks, int B, int H, int W, void* stream);
 
 #ifdef __cplusplus
 }

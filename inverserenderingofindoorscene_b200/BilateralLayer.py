@@ -14,6 +14,8 @@
 BilateralLayer.py:44,79), which current SciPy rejects; this build uses the INTENDED preset
 ``bs_params_arr[3]`` (12/10/10/10).  ``CG_MAXITER_OVERRIDE`` forces another integer.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -21,6 +23,7 @@ import torch.nn.functional as F
 from . import _lib
 
 REQUIRES_CONF_GRAD = True   # BilateralLayer.py:17
+_POISON = int(os.environ['IRB_DEBUG_POISON'], 0) if os.environ.get('IRB_DEBUG_POISON') else None
 CG_MAXITER_OVERRIDE = None  # int to force the PCG iteration count
 
 
@@ -84,6 +87,10 @@ class BilateralFunction(torch.autograd.Function):
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         out = torch.empty(B, ch, H, W, dtype=torch.float32, device=dev)
         yhat = torch.empty(B, ch, H * W, dtype=torch.float64, device=dev)
+        if _POISON is not None:     # debugging aid (IRB_DEBUG_POISON=<byte>): results must not depend on uninitialised memory
+            ws.fill_(_POISON)
+            out.view(torch.uint8).fill_(_POISON)
+            yhat.view(torch.uint8).fill_(_POISON)
         with torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
             _lib.check(lib.irb_bg_build(_lib.ptr(image_c), 255.0, B, H, W, sl, sc, ss, _lib.ptr(ws), nbytes, None, st),

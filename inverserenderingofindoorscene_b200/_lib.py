@@ -27,6 +27,8 @@ SIGNATURES = {
     'irb_render_sg_bwd': [_P] * 15 + [_I, _I, _I, _I, _I, _I, _F, _I, _P],
     'irb_avgpool_fwd': [_P, _P, _I, _I, _I, _I, _I, _P],
     'irb_avgpool_bwd': [_P, _P, _I, _I, _I, _I, _I, _P],
+    'irb_avgpool3_fwd': [_P] * 6 + [_I] * 7 + [_P],
+    'irb_avgpool3_bwd': [_P] * 6 + [_I] * 7 + [_P],
     'irb_lsregress_diffspec': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, C.c_longlong, _P],
     'irb_render_loss_fwd': [_P] * 9 + [_I, _I, C.c_longlong, _P],
     'irb_render_loss_bwd': [_P] * 5 + [_I, _I, C.c_longlong, _P],
@@ -37,6 +39,9 @@ SIGNATURES = {
     'irb_bg_workspace_bytes': [_I, _I, _I, _I],
     'irb_bg_build': [_P, _F, _I, _I, _I, _D, _D, _D, _P, C.c_size_t, C.POINTER(C.c_int), _P],
     'irb_bg_vertex_index': [_P, _P, _I, _I, _I, _P],
+    'irb_bg_apply': [_P, _I, _P, _P, _I, _I, _I, _I, _P],
+    'irb_bg_bistochastization': [_P, _P, _P, _I, _I, _I, _P],
+    'irb_bg_stats': [_P, _P, _P, _I, _I, _I, _P],
     'irb_bg_solve_fwd': [_P, _P, _P, _I, _I, _I, _I, _D, _D, _D, _I, _P, _P, _P],
     'irb_bg_solve_bwd': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _D, _D, _D, _I, _P, _P, _P],
 }

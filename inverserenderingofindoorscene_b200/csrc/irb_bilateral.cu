@@ -685,6 +685,51 @@ extern "C" size_t irb_bg_workspace_bytes(int B, int H, int W, int ch) {
     return make_layout(B, H, W, ch).total;
 }
 
+// ---------------------------------------------------------------------------------------------
+// 6. primitive operators of the grid facade (BilateralGrid.py:90-107): splat = S x (ordered segmented sums, the CSR
+//    product's summation order), slice = S^T y, blur = 2 dim y + sum_dims B_dim y.  fp64 in / out like the reference.
+//    op 0 splat: x [B,ch,P] per pixel -> out [B,ch,P] per vertex (entries >= V zeroed); 1 slice; 2 blur (vertex -> vertex)
+// ---------------------------------------------------------------------------------------------
+__global__ void bg_op_kernel(const void* ws, BgLayout L, int op, const double* __restrict__ x, double* __restrict__ out) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    const size_t P = L.P;
+    if (t >= P) return;
+    const int V = at<int>(ws, L.hdr)[b];
+    for (int c = 0; c < L.ch; ++c) {
+        const double* xc = x + ((size_t)b * L.ch + c) * P;
+        double* oc = out + ((size_t)b * L.ch + c) * P;
+        if (op == 1) {
+            oc[t] = xc[at<int>(ws, L.idx)[(size_t)b * P + t]];
+        } else if (t >= (size_t)V) {
+            oc[t] = 0.0;
+        } else if (op == 0) {
+            const int* vs = at<int>(ws, L.vstart) + (size_t)b * (P + 1);
+            const int* sp = at<int>(ws, L.payB) + (size_t)b * P;
+            double acc = 0.0;
+            for (int i = vs[t]; i < vs[t + 1]; ++i) acc += xc[sp[i]];
+            oc[t] = acc;
+        } else {
+            oc[t] = bg_blur(xc, at<int>(ws, L.nbr) + (size_t)b * 2 * BG_DIM * P, P, t);
+        }
+    }
+}
+
+// directed neighbour links per image (E of SURVEY 8d)
+__global__ void bg_links_kernel(const void* ws, BgLayout L, unsigned long long* __restrict__ links) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    const size_t P = L.P;
+    int cnt = 0;
+    if (t < (size_t)at<int>(ws, L.hdr)[b]) {
+        const int* nbr = at<int>(ws, L.nbr) + (size_t)b * 2 * BG_DIM * P;
+        for (int d = 0; d < 2 * BG_DIM; ++d) cnt += nbr[(size_t)d * P + t] >= 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(links + b, (unsigned long long)cnt);
+}
+
 static int bg_check(const void* ws, int B, int H, int W, int ch, const char* who) {
     IRB_REQUIRE(ws != nullptr, "%s: null workspace", who);
     IRB_REQUIRE(B > 0 && H > 0 && W > 0, "%s: non-positive shape", who);
@@ -780,4 +825,44 @@ extern "C" int irb_bg_solve_bwd(void* ws, const float* pred, const float* conf, 
     const dim3 grid((unsigned)((L.P + 255) / 256), (unsigned)B);
     bg_grad_kernel<<<grid, 256, 0, st>>>(ws, L, gh, yhat, pred, conf, g_pred, g_conf);
     return check_launch("bg_solve_bwd");
+}
+
+extern "C" int irb_bg_apply(const void* ws, int op, const double* x, double* out, int B, int ch, int H, int W, void* stream) {
+    if (int rc = bg_check(ws, B, H, W, ch, "bg_apply")) return rc;
+    IRB_REQUIRE(x && out && x != out, "bg_apply: null or aliased pointer");
+    IRB_REQUIRE(op >= 0 && op <= 2, "bg_apply: op must be 0 (splat), 1 (slice) or 2 (blur)");
+    const BgLayout L = make_layout(B, H, W, ch);
+    const dim3 grid((unsigned)((L.P + 255) / 256), (unsigned)B);
+    bg_op_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ws, L, op, x, out);
+    return check_launch("bg_apply");
+}
+
+extern "C" int irb_bg_bistochastization(const void* ws, double* n, double* m, int B, int H, int W, void* stream) {
+    if (int rc = bg_check(ws, B, H, W, 1, "bg_bistochastization")) return rc;
+    IRB_REQUIRE(n && m, "bg_bistochastization: null pointer");
+    const BgLayout L = make_layout(B, H, W, 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyAsync(n, at<double>(ws, L.n0), 8 * L.P * (size_t)B, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(m, at<double>(ws, L.m), 8 * L.P * (size_t)B, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) {
+        set_error("bg_bistochastization: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+extern "C" int irb_bg_stats(const void* ws, int* nverts, unsigned long long* nlinks, int B, int H, int W, void* stream) {
+    if (int rc = bg_check(ws, B, H, W, 1, "bg_stats")) return rc;
+    IRB_REQUIRE(nverts && nlinks, "bg_stats: null pointer");
+    const BgLayout L = make_layout(B, H, W, 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(nlinks, 0, 8 * (size_t)B, st);
+    const dim3 grid((unsigned)((L.P + 255) / 256), (unsigned)B);
+    bg_links_kernel<<<grid, 256, 0, st>>>(ws, L, nlinks);
+    const cudaError_t e = cudaMemcpyAsync(nverts, at<int>(ws, L.hdr), 4 * (size_t)B, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) {
+        set_error("bg_stats: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    return check_launch("bg_stats");
 }

@@ -7,6 +7,7 @@
 // drop-ins for callers that hand forwardEnv an arbitrary env tensor; the fused kernel in
 // irb_render_sg.cu is the fast path when the env-map comes from SG lobes.
 #include "irb_common.cuh"
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -105,6 +106,7 @@ extern "C" int irb_sg_to_env_fwd(const float* axis, const float* lamb, const flo
                                  float* weight_w, int B, int K, int R, int C, int envH, int envW, int warp, void* stream) {
     IRB_REQUIRE(B > 0 && K > 0 && R > 0 && C > 0, "sg_to_env_fwd: non-positive shape");
     IRB_REQUIRE(axis && lamb && weight && env, "sg_to_env_fwd: null pointer");
+    IRB_REQUIRE(((uintptr_t)env & 15u) == 0, "sg_to_env_fwd: env must be 16-byte aligned (it is written as 16-byte vectors)");
     EnvTab tab;
     if (int rc = mk_tab(tab, envH, envW, B, "sg_to_env_fwd")) return rc;
     SgEnvArgs s{};
@@ -127,6 +129,7 @@ extern "C" int irb_sg_to_env_bwd(const float* axis, const float* lamb, const flo
                                  int envW, int warp, void* stream) {
     IRB_REQUIRE(B > 0 && K > 0 && R > 0 && C > 0, "sg_to_env_bwd: non-positive shape");
     IRB_REQUIRE(axis && lamb && weight && g_env, "sg_to_env_bwd: null pointer");
+    IRB_REQUIRE(((uintptr_t)g_env & 15u) == 0, "sg_to_env_bwd: g_env must be 16-byte aligned (it is read as 16-byte vectors)");
     EnvTab tab;
     if (int rc = mk_tab(tab, envH, envW, B, "sg_to_env_bwd")) return rc;
     SgEnvArgs s{};
@@ -217,6 +220,7 @@ extern "C" int irb_render_env_fwd(const float* albedo, const float* normal, cons
                                   int envW, float F0, void* stream) {
     IRB_REQUIRE(B > 0 && R > 0 && C > 0, "render_env_fwd: non-positive shape");
     IRB_REQUIRE(albedo && normal && rough && env && view && out_diff && out_spec, "render_env_fwd: null pointer");
+    IRB_REQUIRE(((uintptr_t)env & 15u) == 0, "render_env_fwd: env must be 16-byte aligned (it is read as 16-byte vectors)");
     EnvTab tab;
     if (int rc = mk_tab(tab, envH, envW, B, "render_env_fwd")) return rc;
     RenderEnvArgs s{};
@@ -234,6 +238,7 @@ extern "C" int irb_render_env_bwd(const float* albedo, const float* normal, cons
                                   float F0, void* stream) {
     IRB_REQUIRE(B > 0 && R > 0 && C > 0, "render_env_bwd: non-positive shape");
     IRB_REQUIRE(albedo && normal && rough && env && view && g_diff && g_spec, "render_env_bwd: null pointer");
+    IRB_REQUIRE((((uintptr_t)env | (uintptr_t)g_env) & 15u) == 0, "render_env_bwd: env / g_env must be 16-byte aligned");
     EnvTab tab;
     if (int rc = mk_tab(tab, envH, envW, B, "render_env_bwd")) return rc;
     RenderEnvArgs s{};

@@ -30,6 +30,27 @@ __device__ __forceinline__ void ls_coefs(const double* st, double count, float& 
     cS = (float)fmin(fmax(ok ? c2 : 0.0, 0.0), 1000.0);
 }
 
+// The streaming kernels below read 16-byte vectors when every plane allows it (VEC = 4: n % 4 == 0, 16-byte aligned bases;
+// the first version read scalars and sat at ~1.3 TB/s, 80 % of its samples on long-scoreboard stalls -- profiles/r02).
+template <int VEC> struct Vf;
+template <> struct Vf<1> { float v[1]; };
+template <> struct Vf<4> { float v[4]; };
+template <int VEC> __device__ __forceinline__ Vf<VEC> ldv(const float* p, size_t i) {
+    Vf<VEC> r;
+    if (VEC == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+        r.v[0] = t.x; r.v[1 % VEC] = t.y; r.v[2 % VEC] = t.z; r.v[3 % VEC] = t.w;
+    } else {
+        r.v[0] = __ldg(p + i);
+    }
+    return r;
+}
+template <int VEC> __device__ __forceinline__ void stv(float* p, size_t i, const Vf<VEC>& r) {
+    if (VEC == 4) reinterpret_cast<float4*>(p)[i] = make_float4(r.v[0], r.v[1 % VEC], r.v[2 % VEC], r.v[3 % VEC]);
+    else p[i] = r.v[0];
+}
+
+template <int VEC>
 __global__ void lsreg_stats1_kernel(const float* __restrict__ d, const float* __restrict__ s, const float* __restrict__ im,
                                     double* __restrict__ stats, size_t n) {
     const int b = blockIdx.y;
@@ -37,15 +58,19 @@ __global__ void lsreg_stats1_kernel(const float* __restrict__ d, const float* __
     const float* sp = s + (size_t)b * n;
     const float* ip = im + (size_t)b * n;
     float a11 = 0, a22 = 0, a12 = 0, b1 = 0, b2 = 0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float iv = ip[i];
-        const float m = iv < 0.9f ? 1.f : 0.f;
-        const float dv = dp[i] * m, sv = sp[i] * m, imv = iv * m;
-        a11 += dv * dv;
-        a22 += sv * sv;
-        a12 += dv * sv;
-        b1 += dv * imv;
-        b2 += sv * imv;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / VEC; i += (size_t)gridDim.x * blockDim.x) {
+        const Vf<VEC> iv4 = ldv<VEC>(ip, i), dv4 = ldv<VEC>(dp, i), sv4 = ldv<VEC>(sp, i);
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) {
+            const float iv = iv4.v[u];
+            const float m = iv < 0.9f ? 1.f : 0.f;
+            const float dv = dv4.v[u] * m, sv = sv4.v[u] * m, imv = iv * m;
+            a11 += dv * dv;
+            a22 += sv * sv;
+            a12 += dv * sv;
+            b1 += dv * imv;
+            b2 += sv * imv;
+        }
     }
     double* st = stats + (size_t)b * 8;
     block_sum_atomic(a11, st + 0);
@@ -55,6 +80,7 @@ __global__ void lsreg_stats1_kernel(const float* __restrict__ d, const float* __
     block_sum_atomic(b2, st + 4);
 }
 
+template <int VEC>
 __global__ void lsreg_stats2_kernel(const float* __restrict__ d, const float* __restrict__ s, const float* __restrict__ im,
                                     double* __restrict__ stats, size_t n) {
     const int b = blockIdx.y;
@@ -64,16 +90,21 @@ __global__ void lsreg_stats2_kernel(const float* __restrict__ d, const float* __
     const float* sp = s + (size_t)b * n;
     const float* ip = im + (size_t)b * n;
     float ri = 0, rr = 0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float r = __saturatef(cD * dp[i] + cS * sp[i]);
-        ri += r * ip[i];
-        rr += r * r;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / VEC; i += (size_t)gridDim.x * blockDim.x) {
+        const Vf<VEC> iv4 = ldv<VEC>(ip, i), dv4 = ldv<VEC>(dp, i), sv4 = ldv<VEC>(sp, i);
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) {
+            const float r = __saturatef(cD * dv4.v[u] + cS * sv4.v[u]);
+            ri += r * iv4.v[u];
+            rr += r * r;
+        }
     }
     double* st = stats + (size_t)b * 8;
     block_sum_atomic(ri, st + 5);
     block_sum_atomic(rr, st + 6);
 }
 
+template <int VEC>
 __global__ void lsreg_apply_kernel(const float* __restrict__ d, const float* __restrict__ s, const double* __restrict__ stats,
                                    float* __restrict__ od, float* __restrict__ os, float* __restrict__ coef, size_t n) {
     const int b = blockIdx.y;
@@ -86,10 +117,30 @@ __global__ void lsreg_apply_kernel(const float* __restrict__ d, const float* __r
         coef[2 * b] = kd;
         coef[2 * b + 1] = ks;
     }
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        od[(size_t)b * n + i] = kd * d[(size_t)b * n + i];
-        os[(size_t)b * n + i] = ks * s[(size_t)b * n + i];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / VEC; i += (size_t)gridDim.x * blockDim.x) {
+        Vf<VEC> dv = ldv<VEC>(d + (size_t)b * n, i), sv = ldv<VEC>(s + (size_t)b * n, i);
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) {
+            dv.v[u] *= kd;
+            sv.v[u] *= ks;
+        }
+        stv<VEC>(od + (size_t)b * n, i, dv);
+        stv<VEC>(os + (size_t)b * n, i, sv);
     }
+}
+
+// launch geometry of the streaming kernels: one 16-byte (or 4-byte) item per thread and trip, ~2 trips per thread
+static inline dim3 stream_grid(size_t items, int B) {
+    size_t gx = (items + 256 * 2 - 1) / (256 * 2);
+    if (gx < 1) gx = 1;
+    if (gx > 4096) gx = 4096;
+    return dim3((unsigned)gx, (unsigned)B);
+}
+template <typename... P> static inline bool aligned16(P... p) {
+    uintptr_t m = 0;
+    const uintptr_t a[] = {(uintptr_t)p...};
+    for (uintptr_t x : a) m |= x;
+    return (m & 15u) == 0;
 }
 
 }  // namespace irb
@@ -104,13 +155,17 @@ extern "C" int irb_lsregress_diffspec(const float* diff, const float* spec, cons
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)n_per_sample;
     cudaMemsetAsync(stats, 0, sizeof(double) * 8 * (size_t)B, st);
-    unsigned gx = (unsigned)((n + 256 * 8 - 1) / (256 * 8));
-    if (gx < 1) gx = 1;
-    if (gx > 1024) gx = 1024;
-    const dim3 grid(gx, (unsigned)B);
-    lsreg_stats1_kernel<<<grid, 256, 0, st>>>(diff, spec, im, stats, n);
-    lsreg_stats2_kernel<<<grid, 256, 0, st>>>(diff_orig, spec_orig, im, stats, n);  // models.py:66-72: on the scaled *Orig tensors
-    lsreg_apply_kernel<<<grid, 256, 0, st>>>(diff_orig, spec_orig, stats, out_diff, out_spec, coef, n);
+    if (n % 4 == 0 && aligned16(diff, spec, im, diff_orig, spec_orig, out_diff, out_spec)) {
+        const dim3 grid = stream_grid(n / 4, B);
+        lsreg_stats1_kernel<4><<<grid, 256, 0, st>>>(diff, spec, im, stats, n);
+        lsreg_stats2_kernel<4><<<grid, 256, 0, st>>>(diff_orig, spec_orig, im, stats, n);  // models.py:66-72: on the scaled *Orig tensors
+        lsreg_apply_kernel<4><<<grid, 256, 0, st>>>(diff_orig, spec_orig, stats, out_diff, out_spec, coef, n);
+    } else {
+        const dim3 grid = stream_grid(n, B);
+        lsreg_stats1_kernel<1><<<grid, 256, 0, st>>>(diff, spec, im, stats, n);
+        lsreg_stats2_kernel<1><<<grid, 256, 0, st>>>(diff_orig, spec_orig, im, stats, n);
+        lsreg_apply_kernel<1><<<grid, 256, 0, st>>>(diff_orig, spec_orig, stats, out_diff, out_spec, coef, n);
+    }
     return check_launch("lsregress_diffspec", 3);
 }
 
@@ -123,6 +178,7 @@ extern "C" int irb_lsregress_diffspec(const float* diff, const float* spec, cons
 // ---------------------------------------------------------------------------------------------
 namespace irb {
 
+template <int VEC>
 __global__ void render_loss_kernel(const float* __restrict__ d, const float* __restrict__ s, const float* __restrict__ im,
                                    const float* __restrict__ seg, const double* __restrict__ stats, float* __restrict__ rendered,
                                    float* __restrict__ gbase, float* __restrict__ coef, double* __restrict__ terms, size_t n,
@@ -139,31 +195,46 @@ __global__ void render_loss_kernel(const float* __restrict__ d, const float* __r
     }
     const float* sg = seg + (size_t)b * npix;
     float num = 0.f, cnt = 0.f;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t o = (size_t)b * n + i;
-        const float m = sg[i % npix];
-        const float x = kd * d[o] + ks * s[o];
-        const float r = __saturatef(x);
-        const float e = r - im[o];
-        num += e * e * m;
-        if (i < npix) cnt += m;
-        if (rendered) rendered[o] = r;
-        if (gbase) gbase[o] = (x >= 0.f && x <= 1.f) ? 2.f * e * m : 0.f;
+    // VEC == 4 requires npix % 4 == 0, so the four elements of a vector share one channel and consecutive pixels
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / VEC; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t e0 = i * VEC;
+        const Vf<VEC> dv = ldv<VEC>(d + (size_t)b * n, i), sv = ldv<VEC>(s + (size_t)b * n, i), iv = ldv<VEC>(im + (size_t)b * n, i);
+        const Vf<VEC> mv = ldv<VEC>(sg, (e0 % npix) / VEC);
+        Vf<VEC> rv, gv;
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) {
+            const float m = mv.v[u];
+            const float x = kd * dv.v[u] + ks * sv.v[u];
+            const float r = __saturatef(x);
+            const float e = r - iv.v[u];
+            num += e * e * m;
+            if (e0 < npix) cnt += m;
+            rv.v[u] = r;
+            gv.v[u] = (x >= 0.f && x <= 1.f) ? 2.f * e * m : 0.f;
+        }
+        if (rendered) stv<VEC>(rendered + (size_t)b * n, i, rv);
+        if (gbase) stv<VEC>(gbase + (size_t)b * n, i, gv);
     }
     block_sum_atomic(num, terms);
     block_sum_atomic(cnt, terms + 1);
 }
 
+template <int VEC>
 __global__ void render_loss_seed_kernel(const float* __restrict__ gbase, const float* __restrict__ coef, const float* __restrict__ g_num,
                                         float* __restrict__ g_diff, float* __restrict__ g_spec, size_t n) {
     const int b = blockIdx.y;
     const float gn = g_num ? *g_num : 1.f;
     const float kd = gn * coef[2 * b], ks = gn * coef[2 * b + 1];
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t o = (size_t)b * n + i;
-        const float g = gbase[o];
-        if (g_diff) g_diff[o] = kd * g;
-        if (g_spec) g_spec[o] = ks * g;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / VEC; i += (size_t)gridDim.x * blockDim.x) {
+        const Vf<VEC> g = ldv<VEC>(gbase + (size_t)b * n, i);
+        Vf<VEC> a, c;
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) {
+            a.v[u] = kd * g.v[u];
+            c.v[u] = ks * g.v[u];
+        }
+        if (g_diff) stv<VEC>(g_diff + (size_t)b * n, i, a);
+        if (g_spec) stv<VEC>(g_spec + (size_t)b * n, i, c);
     }
 }
 
@@ -178,13 +249,17 @@ extern "C" int irb_render_loss_fwd(const float* diff, const float* spec, const f
     const size_t n = (size_t)n_pix * (size_t)ch;
     cudaMemsetAsync(stats, 0, sizeof(double) * 8 * (size_t)B, st);
     cudaMemsetAsync(terms, 0, sizeof(double) * 2, st);
-    unsigned gx = (unsigned)((n + 256 * 8 - 1) / (256 * 8));
-    if (gx < 1) gx = 1;
-    if (gx > 1024) gx = 1024;
-    const dim3 grid(gx, (unsigned)B);
-    lsreg_stats1_kernel<<<grid, 256, 0, st>>>(diff, spec, im, stats, n);
-    lsreg_stats2_kernel<<<grid, 256, 0, st>>>(diff, spec, im, stats, n);
-    render_loss_kernel<<<grid, 256, 0, st>>>(diff, spec, im, seg, stats, rendered, gbase, coef, terms, n, (size_t)n_pix);
+    if (n_pix % 4 == 0 && aligned16(diff, spec, im, seg, rendered, gbase)) {
+        const dim3 grid = stream_grid(n / 4, B);
+        lsreg_stats1_kernel<4><<<grid, 256, 0, st>>>(diff, spec, im, stats, n);
+        lsreg_stats2_kernel<4><<<grid, 256, 0, st>>>(diff, spec, im, stats, n);
+        render_loss_kernel<4><<<grid, 256, 0, st>>>(diff, spec, im, seg, stats, rendered, gbase, coef, terms, n, (size_t)n_pix);
+    } else {
+        const dim3 grid = stream_grid(n, B);
+        lsreg_stats1_kernel<1><<<grid, 256, 0, st>>>(diff, spec, im, stats, n);
+        lsreg_stats2_kernel<1><<<grid, 256, 0, st>>>(diff, spec, im, stats, n);
+        render_loss_kernel<1><<<grid, 256, 0, st>>>(diff, spec, im, seg, stats, rendered, gbase, coef, terms, n, (size_t)n_pix);
+    }
     return check_launch("render_loss_fwd", 3);
 }
 
@@ -194,10 +269,10 @@ extern "C" int irb_render_loss_bwd(const float* gbase, const float* coef, const 
     IRB_REQUIRE(B > 0 && B <= 65535 && ch > 0 && n_pix > 0, "render_loss_bwd: bad shape");
     if (!g_diff && !g_spec) return 0;
     const size_t n = (size_t)n_pix * (size_t)ch;
-    unsigned gx = (unsigned)((n + 256 * 8 - 1) / (256 * 8));
-    if (gx < 1) gx = 1;
-    if (gx > 1024) gx = 1024;
-    render_loss_seed_kernel<<<dim3(gx, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(gbase, coef, g_num, g_diff, g_spec, n);
+    if (n % 4 == 0 && aligned16(gbase, g_diff, g_spec))
+        render_loss_seed_kernel<4><<<stream_grid(n / 4, B), 256, 0, (cudaStream_t)stream>>>(gbase, coef, g_num, g_diff, g_spec, n);
+    else
+        render_loss_seed_kernel<1><<<stream_grid(n, B), 256, 0, (cudaStream_t)stream>>>(gbase, coef, g_num, g_diff, g_spec, n);
     return check_launch("render_loss_bwd");
 }
 

@@ -15,11 +15,14 @@
 // irb_driver.cuh (group_general_pixel below).
 #pragma once
 
+// A/B knobs (measured on B200, profiles/r02): rotating the backward loop so that the next pair's forward chain sits beside the
+// current pair's backward chain, and pipelining the forward chain one pair ahead, were both 2-3 % SLOWER than ptxas' own
+// schedule of the plain loops (bwd 1.926 vs 1.883 ms, fwd 0.854 vs 0.826 ms) -> off.
 #ifndef IRB_BWD_ROTATE
-#define IRB_BWD_ROTATE 1
+#define IRB_BWD_ROTATE 0
 #endif
 #ifndef IRB_FWD_PIPE
-#define IRB_FWD_PIPE 1
+#define IRB_FWD_PIPE 0
 #endif
 
 namespace irb {

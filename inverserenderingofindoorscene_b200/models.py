@@ -72,6 +72,46 @@ class _AvgPool(torch.autograd.Function):
         return gi, None, None
 
 
+class _AvgPool3(torch.autograd.Function):
+    """albedo / normal / rough pooled to the env grid in ONE launch each way (irb_avgpool3_fwd/bwd, models.py:465-469)."""
+
+    @staticmethod
+    def forward(ctx, a, n, r, R, C):
+        a, n, r = _c(a), _c(n), _c(r)
+        B, _, H, W = a.shape
+        outs = [torch.empty(B, t.shape[1], R, C, device=a.device, dtype=a.dtype) for t in (a, n, r)]
+        with torch.cuda.device(a.device):
+            _lib.check(_lib.lib().irb_avgpool3_fwd(_lib.ptr(a), _lib.ptr(n), _lib.ptr(r), *[_lib.ptr(o) for o in outs],
+                                                   B * a.shape[1], B * n.shape[1], B * r.shape[1], H, W, R, C,
+                                                   _lib.stream_ptr(a.device)), 'irb_avgpool3_fwd')
+        ctx.dims = (B, a.shape[1], n.shape[1], r.shape[1], H, W, R, C)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, ga, gn, gr):
+        B, ca, cn, cr, H, W, R, C = ctx.dims
+        need = ctx.needs_input_grad
+        gs = [(_c(g) if (g is not None and need[i]) else None) for i, g in enumerate((ga, gn, gr))]
+        ref = next((g for g in gs if g is not None), None)
+        if ref is None:
+            return None, None, None, None, None
+        gi = [torch.empty(B, c, H, W, device=ref.device, dtype=ref.dtype) if g is not None else None
+              for g, c in zip(gs, (ca, cn, cr))]
+        with torch.cuda.device(ref.device):
+            _lib.check(_lib.lib().irb_avgpool3_bwd(*[_lib.ptr(g) for g in gs], *[_lib.ptr(g) for g in gi], B * ca, B * cn, B * cr,
+                                                   H, W, R, C, _lib.stream_ptr(ref.device)), 'irb_avgpool3_bwd')
+        return gi[0], gi[1], gi[2], None, None
+
+
+def _pool3(a, n, r, R, C):
+    """the three BRDF maps at the env-grid resolution (identity when they already are)"""
+    if a.shape[2:] == n.shape[2:] == r.shape[2:]:
+        if a.shape[2] == R and a.shape[3] == C:
+            return a, n, r
+        return _AvgPool3.apply(a, n, r, R, C)
+    return _pool(a, R, C), _pool(n, R, C), _pool(r, R, C)
+
+
 def _pool(x, R, C):
     if x.shape[2] == R and x.shape[3] == C:
         return x
@@ -371,6 +411,9 @@ class output2env():
                                     float(offset))
 
 
+_LAYER_TABLES = {}   # geometry -> (v, pCoord, up, ls, envWeight), see renderingLayer.__init__
+
+
 class renderingLayer():
     """SG-lit microfacet shading.  Mirror of models.renderingLayer (models.py:407-522)."""
 
@@ -386,6 +429,19 @@ class renderingLayer():
         self.xRange = 1 * np.tan(self.fov / 2)
         self.yRange = float(imHeight) / float(imWidth) * self.xRange
         self.isCuda = isCuda
+        # testReal.py:341-346 builds a new layer for every image with that image's (H, W, fov): the constant tables are
+        # cached per geometry (host arithmetic + 5 H2D copies happen once; afterwards construction is a dict lookup)
+        key = (imWidth, imHeight, float(fov), tuple(float(x) for x in np.asarray(cameraPos).reshape(-1)), envWidth, envHeight,
+               bool(isCuda), torch.cuda.current_device() if isCuda else -1)
+        tabs = _LAYER_TABLES.get(key)
+        if tabs is None:
+            if len(_LAYER_TABLES) > 64:
+                _LAYER_TABLES.clear()
+            tabs = _LAYER_TABLES[key] = self._make_tables(isCuda)
+        self.v, self.pCoord, self.up, self.ls, self.envWeight = tabs
+
+    def _make_tables(self, isCuda):
+        imWidth, imHeight, envWidth, envHeight = self.imWidth, self.imHeight, self.envWidth, self.envHeight
         # pixel centres on the z=-1 plane, y up (models.py:421-426); unit view vectors (:428-430)
         xs = np.linspace(-self.xRange, self.xRange, imWidth)
         ys = np.linspace(-self.yRange, self.yRange, imHeight)[::-1]
@@ -393,20 +449,17 @@ class renderingLayer():
         pc = np.stack([gx, gy, -np.ones((imHeight, imWidth), dtype=np.float32)]).astype(np.float32)[np.newaxis]
         vv = self.cameraPos - pc
         vv = (vv / np.sqrt(np.maximum(np.sum(vv * vv, axis=1), 1e-12)[:, np.newaxis, :, :])).astype(np.float32)
-        self.v = torch.from_numpy(vv)
-        self.pCoord = torch.from_numpy(pc)
-        self.up = torch.Tensor([0, 1, 0])
+        v = torch.from_numpy(vv)
+        pCoord = torch.from_numpy(pc)
+        up = torch.Tensor([0, 1, 0])
         lx, ly, lz, el = _direction_table(envWidth, envHeight)
         ls = np.stack([lx.reshape(-1), ly.reshape(-1), lz.reshape(-1)], axis=1)
         ew = np.sin(el.reshape(-1, 1)) * np.pi * np.pi / envWidth / envHeight
-        self.ls = torch.from_numpy(ls.astype(np.float32))
-        self.envWeight = torch.from_numpy(ew.astype(np.float32)).unsqueeze(0).unsqueeze(-1).unsqueeze(-1)
+        ls = torch.from_numpy(ls.astype(np.float32))
+        envWeight = torch.from_numpy(ew.astype(np.float32)).unsqueeze(0).unsqueeze(-1).unsqueeze(-1)
         if isCuda:
-            self.v = self.v.cuda()
-            self.pCoord = self.pCoord.cuda()
-            self.up = self.up.cuda()
-            self.ls = self.ls.cuda()
-            self.envWeight = self.envWeight.cuda()
+            v, pCoord, up, ls, envWeight = v.cuda(), pCoord.cuda(), up.cuda(), ls.cuda(), envWeight.cuda()
+        return v, pCoord, up, ls, envWeight
 
     # -- helpers -----------------------------------------------------------------------------
     def _view(self, dev):
@@ -456,9 +509,7 @@ class renderingLayer():
             envmap = envmap.materialize()
         _chk(envmap, 'envmap', 6)
         dev = envmap.device
-        A = _pool(diffusePred, R, C)
-        N = _pool(normalPred, R, C)
-        Rg = _pool(roughPred, R, C)
+        A, N, Rg = _pool3(diffusePred, normalPred, roughPred, R, C)
         return _RenderEnv.apply(A, N, Rg, envmap, self._view(dev), self.F0)
 
     # -- fused entry point (superset of the reference API) -------------------------------------
@@ -473,9 +524,7 @@ class renderingLayer():
         B, K, _, R, C = axisOrig.shape
         self._check_maps(diffusePred, normalPred, roughPred, R, C)
         dev = axisOrig.device
-        A = _pool(diffusePred, R, C)
-        N = _pool(normalPred, R, C)
-        Rg = _pool(roughPred, R, C)
+        A, N, Rg = _pool3(diffusePred, normalPred, roughPred, R, C)
         return _RenderSG.apply(A, N, Rg, axisOrig, lambOrig, weightOrig, self._view(dev), self.F0,
                                self.envHeight, self.envWidth, warp)
 
