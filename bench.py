@@ -41,6 +41,9 @@ def parse():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile', default=None, metavar='DIR',
+                    help='capture `ncu --set full` of the fused kernels of THIS command (1 GPU) and write DIR/ncu_metrics.json + '
+                         'ncu_summary.txt (e.g. profiles/r02) -- the file the roofline traffic / pipe fields are read from')
     ap.add_argument('--no-extras', action='store_true', help='skip the secondary configs (bilateral, config 3/5, torch-CUDA reference)')
     ap.add_argument('--cpu-baseline-rows', type=int, default=0, help='rows of the 240x320 frame for the CPU sample (0=auto)')
     return ap.parse_args()
@@ -543,8 +546,23 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_profile(args):
+    """ncu replays every captured kernel ~40x: never a timing run, never multi-rank"""
+    tool = os.path.join(ROOT, 'tools', 'ncu_profile.py')
+    scratch = os.path.join(ROOT, 'gpurun_out', 'ncu_bench')
+    cmd = [sys.executable, tool, 'capture', '--out', scratch, '--kernels', 'render_sg_group_kernel|render_loss|lsreg', '--skip',
+           '20', '--count', '6', '--', sys.executable, os.path.join(ROOT, 'bench.py'), '--steps', '2', '--warmup', '3',
+           '--no-extras', '--no-cpu-baseline']
+    rc = subprocess.run(cmd).returncode
+    if rc == 0:
+        rc = subprocess.run([sys.executable, tool, 'summarize', os.path.join(scratch, 'prof.ncu-rep'), '--out', args.profile]).returncode
+    sys.exit(rc)
+
+
 def main():
     args = parse()
+    if args.profile:
+        run_profile(args)
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -15,6 +15,7 @@ BilateralLayer.py:44,79), which current SciPy rejects; this build uses the INTEN
 ``bs_params_arr[3]`` (12/10/10/10).  ``CG_MAXITER_OVERRIDE`` forces another integer.
 """
 import os
+import weakref
 
 import torch
 import torch.nn as nn
@@ -40,13 +41,15 @@ _PARAM_CACHE = {}
 def _host_values(t):
     """the (few) values of a parameter tensor as Python floats.  The reference keeps sigma / lam / tol in device tensors
     (BilateralLayer.py:145-149) and reads them back on every call (.cpu().numpy(), a device sync); here the read-back
-    happens once per (storage, version) and is cached -- no host sync on the steady-state path."""
-    key = (t.data_ptr(), t._version, str(t.device), t.numel())
-    v = _PARAM_CACHE.get(key)
-    if v is None:
-        if len(_PARAM_CACHE) > 256:
-            _PARAM_CACHE.clear()
-        v = _PARAM_CACHE[key] = tuple(float(x) for x in t.detach().cpu().tolist())
+    happens once per tensor OBJECT and version and is cached -- no host sync on the steady-state path.  (Keyed by the
+    object, checked through a weak reference: a new tensor that happens to reuse a freed address never hits a stale entry.)"""
+    ent = _PARAM_CACHE.get(id(t))
+    if ent is not None and ent[0]() is t and ent[1] == t._version:
+        return ent[2]
+    if len(_PARAM_CACHE) > 256:
+        _PARAM_CACHE.clear()
+    v = tuple(float(x) for x in t.detach().cpu().tolist())
+    _PARAM_CACHE[id(t)] = (weakref.ref(t), t._version, v)
     return v
 
 

