@@ -23,8 +23,8 @@ SIGNATURES = {
     'irb_sg_to_env_bwd': [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     'irb_render_env_fwd': [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     'irb_render_env_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
-    'irb_render_sg_fwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _P],
-    'irb_render_sg_bwd': [_P] * 15 + [_I, _I, _I, _I, _I, _I, _F, _I, _P],
+    'irb_render_sg_fwd': [_P] * 10 + [_I, _I, _I, _I, _I, _I, _F, _I, _P],
+    'irb_render_sg_bwd': [_P] * 16 + [_I, _I, _I, _I, _I, _I, _F, _I, _P],
     'irb_avgpool_fwd': [_P, _P, _I, _I, _I, _I, _I, _P],
     'irb_avgpool_bwd': [_P, _P, _I, _I, _I, _I, _I, _P],
     'irb_avgpool3_fwd': [_P] * 6 + [_I] * 7 + [_P],

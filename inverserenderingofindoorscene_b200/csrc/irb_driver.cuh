@@ -29,6 +29,11 @@ struct RenderSgArgs {
     float* g_axis;
     float* g_lamb;
     float* g_weight;
+    // optional [B,2K,R,C] side tensor: plane 2k = U_k = sum_d w_d e_kd, plane 2k+1 = V_k = sum_d w_d spec_d e_kd.
+    // The forward writes it (regular pixels only), the backward then skips the two accumulations per lobe and direction that
+    // would only rebuild these sums (10 % of its FMA-pipe work; HBM has 90 % slack on this path).  NULL = recompute.
+    float* lobe_uv_out;
+    const float* lobe_uv_in;
     int B, K, R, C;
     float F0;
     int warp;

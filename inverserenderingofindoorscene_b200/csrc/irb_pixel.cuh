@@ -143,7 +143,7 @@ __device__ __forceinline__ float lobes_bwd_dir_pk(LobeGradsPk<KC>& g, const Lobe
     return a + b;
 }
 // accumulation phase only (arguments / exponentials precomputed by lobe_exps_pk)
-template <int KC, bool PIX, bool LOBE>
+template <int KC, bool PIX, bool LOBE, bool SAVED = false>
 __device__ __forceinline__ float lobes_bwd_acc_pk(LobeGradsPk<KC>& g, const pk2 (&P2)[KC / 2], const pk2 (&Q2)[KC / 2],
                                                   const pk2 (&arg)[KC / 2], const pk2 (&e)[KC / 2], float wx, float wy, float wz,
                                                   float w, float spec) {
@@ -155,8 +155,10 @@ __device__ __forceinline__ float lobes_bwd_acc_pk(LobeGradsPk<KC>& g, const pk2 
         if (PIX) sQ2 = fma2(Q2[i], e[i], sQ2);
         if (LOBE) {
             const pk2 ew = mul2(e[i], w2);
-            g.U[i] = add2(g.U[i], ew);
-            g.V[i] = fma2(ew, sp2, g.V[i]);
+            if (!SAVED) {   // SAVED: U_k, V_k come from the forward pass (RenderSgArgs::lobe_uv_in)
+                g.U[i] = add2(g.U[i], ew);
+                g.V[i] = fma2(ew, sp2, g.V[i]);
+            }
             const pk2 t = mul2(ew, fma2(sp2, Q2[i], P2[i]));
             g.S[i] = fma2(t, arg[i], g.S[i]);
             g.mx[i] = fma2(t, wx2, g.mx[i]);

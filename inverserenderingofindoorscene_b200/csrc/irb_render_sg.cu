@@ -188,7 +188,7 @@ static int launch_tma(KernelT kernel, const RenderSgArgs& a, const EnvTab& tab, 
 // per-plane bulk copies for A/B runs)
 template <typename KernelT>
 static int launch_group(KernelT kernel, const RenderSgArgs& a, const EnvTab& tab, bool bwd, cudaStream_t st, const char* what,
-                        int tile) {
+                        int tile, bool saved = false) {
     const size_t plane = (size_t)a.R * a.C;
     const size_t tiles_per_img = (plane + tile - 1) / tile;
     const size_t total = tiles_per_img * (size_t)a.B;
@@ -206,9 +206,10 @@ static int launch_group(KernelT kernel, const RenderSgArgs& a, const EnvTab& tab
                   cached_tile_map(&maps.m[4], a.axis, plane, 3 * K, B, T) && cached_tile_map(&maps.m[5], a.lamb, plane, K, B, T) &&
                   cached_tile_map(&maps.m[6], a.weight, plane, 3 * K, B, T);
         if (ok && bwd) ok = cached_tile_map(&maps.m[7], a.g_diff, plane, 3, B, T) && cached_tile_map(&maps.m[8], a.g_spec, plane, 3, B, T);
+        if (ok && saved) ok = cached_tile_map(&maps.m[9], a.lobe_uv_in, plane, 2 * K, B, T);
         maps.on = ok ? 1 : 0;
     }
-    const size_t smem = 2 * (size_t)stage_planes(a.K, bwd) * tile * sizeof(float);
+    const size_t smem = 2 * (size_t)(stage_planes(a.K, bwd) + (saved ? 2 * a.K : 0)) * tile * sizeof(float);
     int per_sm = 1;
     if (int e = persistent_ctas_per_sm(kernel, kThreads, smem, &per_sm)) {
         set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", what, smem, cudaGetErrorString((cudaError_t)e));
@@ -263,11 +264,11 @@ using namespace irb;
 
 extern "C" int irb_render_sg_fwd(const float* albedo, const float* normal, const float* rough, const float* axis,
                                  const float* lamb, const float* weight, const float* view, float* out_diff,
-                                 float* out_spec, int B, int K, int R, int C, int envH, int envW, float F0, int warp,
-                                 void* stream) {
+                                 float* out_spec, float* lobe_uv, int B, int K, int R, int C, int envH, int envW, float F0,
+                                 int warp, void* stream) {
     RenderSgArgs a{};
     a.albedo = albedo; a.normal = normal; a.rough = rough; a.axis = axis; a.lamb = lamb; a.weight = weight; a.view = view;
-    a.out_diff = out_diff; a.out_spec = out_spec;
+    a.out_diff = out_diff; a.out_spec = out_spec; a.lobe_uv_out = lobe_uv;
     a.B = B; a.K = K; a.R = R; a.C = C; a.F0 = F0; a.warp = warp;
     EnvTab tab;
     if (int rc = check_common(a, envH, envW, tab)) return rc;
@@ -295,12 +296,12 @@ extern "C" int irb_render_sg_fwd(const float* albedo, const float* normal, const
 
 extern "C" int irb_render_sg_bwd(const float* albedo, const float* normal, const float* rough, const float* axis,
                                  const float* lamb, const float* weight, const float* view, const float* g_diff,
-                                 const float* g_spec, float* g_albedo, float* g_normal, float* g_rough, float* g_axis,
-                                 float* g_lamb, float* g_weight, int B, int K, int R, int C, int envH, int envW, float F0,
-                                 int warp, void* stream) {
+                                 const float* g_spec, const float* lobe_uv, float* g_albedo, float* g_normal, float* g_rough,
+                                 float* g_axis, float* g_lamb, float* g_weight, int B, int K, int R, int C, int envH, int envW,
+                                 float F0, int warp, void* stream) {
     RenderSgArgs a{};
     a.albedo = albedo; a.normal = normal; a.rough = rough; a.axis = axis; a.lamb = lamb; a.weight = weight; a.view = view;
-    a.g_diff = g_diff; a.g_spec = g_spec;
+    a.g_diff = g_diff; a.g_spec = g_spec; a.lobe_uv_in = lobe_uv;
     a.g_albedo = g_albedo; a.g_normal = g_normal; a.g_rough = g_rough; a.g_axis = g_axis; a.g_lamb = g_lamb; a.g_weight = g_weight;
     a.B = B; a.K = K; a.R = R; a.C = C; a.F0 = F0; a.warp = warp;
     EnvTab tab;
@@ -328,12 +329,20 @@ extern "C" int irb_render_sg_bwd(const float* albedo, const float* normal, const
         const char* w = "render_sg_bwd(group)";
         const char* mb = getenv("IRB_BWD_MINB");  // A/B knob: resident CTAs the full backward is compiled for (2: 255 regs, 3: 168, 4: 128)
         const int minb = (mb && mb[0] >= '2' && mb[0] <= '4') ? mb[0] - '0' : 2;
+        // saved: U_k / V_k of the forward pass are staged with the tile (16-byte alignment like every staged plane)
+        const bool saved = lobe && a.lobe_uv_in != nullptr && (((uintptr_t)a.lobe_uv_in & 15u) == 0);
+        if (!saved) a.lobe_uv_in = nullptr;
 #define IRB_GROUP_BWD(TPP)                                                                                                   \
-    (pix && lobe ? (minb == 4   ? launch_group(render_sg_group_kernel<1, TPP, true, true, 4>, a, tab, true, st, w, kThreads / TPP) \
-                    : minb == 3 ? launch_group(render_sg_group_kernel<1, TPP, true, true, 3>, a, tab, true, st, w, kThreads / TPP) \
-                                : launch_group(render_sg_group_kernel<1, TPP, true, true, 2>, a, tab, true, st, w, kThreads / TPP)) \
-     : pix      ? launch_group(render_sg_group_kernel<1, TPP, true, false, 3>, a, tab, true, st, w, kThreads / TPP)            \
-                : launch_group(render_sg_group_kernel<1, TPP, false, true, 3>, a, tab, true, st, w, kThreads / TPP))
+    (pix && lobe                                                                                                             \
+         ? (saved ? (minb == 4   ? launch_group(render_sg_group_kernel<1, TPP, true, true, 4, true>, a, tab, true, st, w, kThreads / TPP, true) \
+                     : minb == 3 ? launch_group(render_sg_group_kernel<1, TPP, true, true, 3, true>, a, tab, true, st, w, kThreads / TPP, true) \
+                                 : launch_group(render_sg_group_kernel<1, TPP, true, true, 2, true>, a, tab, true, st, w, kThreads / TPP, true)) \
+                  : (minb == 4   ? launch_group(render_sg_group_kernel<1, TPP, true, true, 4>, a, tab, true, st, w, kThreads / TPP) \
+                     : minb == 3 ? launch_group(render_sg_group_kernel<1, TPP, true, true, 3>, a, tab, true, st, w, kThreads / TPP) \
+                                 : launch_group(render_sg_group_kernel<1, TPP, true, true, 2>, a, tab, true, st, w, kThreads / TPP))) \
+     : pix ? launch_group(render_sg_group_kernel<1, TPP, true, false, 3>, a, tab, true, st, w, kThreads / TPP)               \
+           : (saved ? launch_group(render_sg_group_kernel<1, TPP, false, true, 3, true>, a, tab, true, st, w, kThreads / TPP, true) \
+                    : launch_group(render_sg_group_kernel<1, TPP, false, true, 3>, a, tab, true, st, w, kThreads / TPP)))
         if (K <= 6) rc = IRB_GROUP_BWD(1);
         else if (K <= 12) rc = IRB_GROUP_BWD(2);
         else rc = IRB_GROUP_BWD(4);

@@ -27,8 +27,9 @@
 
 namespace irb {
 
+// uv: the backward also stages the 2K planes of the forward's lobe sums (RenderSgArgs::lobe_uv_in) behind the other planes
 __device__ __forceinline__ void issue_tile_n(float* stage, uint64_t* bar, const RenderSgArgs& a, const TileMaps& maps, size_t tile,
-                                             size_t tiles_per_img, bool bwd, int PT) {
+                                             size_t tiles_per_img, bool bwd, int PT, bool uv = false) {
     const int lane = threadIdx.x & 31;
     const size_t plane = (size_t)a.R * a.C;
     const size_t b = tile / tiles_per_img, pix0 = (tile % tiles_per_img) * (size_t)PT;
@@ -37,7 +38,7 @@ __device__ __forceinline__ void issue_tile_n(float* stage, uint64_t* bar, const 
         // per-plane form cost the producer warp ~75 cycles per copy, 11 % of its time, and the other warps waited for it
         if (lane == 0) {
             const int K = a.K;
-            mbar_expect_tx(bar, (uint32_t)stage_planes(K, bwd) * (uint32_t)PT * 4u);
+            mbar_expect_tx(bar, (uint32_t)(stage_planes(K, bwd) + (uv ? 2 * K : 0)) * (uint32_t)PT * 4u);
             const int c0 = (int)pix0, cb = (int)b;
             tma_load_3d(stage, &maps.m[0], c0, 0, cb, bar);
             tma_load_3d(stage + 3 * PT, &maps.m[1], c0, 0, cb, bar);
@@ -49,6 +50,7 @@ __device__ __forceinline__ void issue_tile_n(float* stage, uint64_t* bar, const 
             if (bwd) {
                 tma_load_3d(stage + (10 + 7 * K) * PT, &maps.m[7], c0, 0, cb, bar);
                 tma_load_3d(stage + (13 + 7 * K) * PT, &maps.m[8], c0, 0, cb, bar);
+                if (uv) tma_load_3d(stage + (16 + 7 * K) * PT, &maps.m[9], c0, 0, cb, bar);
             }
         }
         return;
@@ -56,7 +58,7 @@ __device__ __forceinline__ void issue_tile_n(float* stage, uint64_t* bar, const 
     const uint32_t valid = (uint32_t)((plane - pix0) < (size_t)PT ? (plane - pix0) : (size_t)PT);
     const uint32_t bytes = valid * 4u;
     const int K = a.K;
-    const int np = stage_planes(K, bwd);
+    const int np = stage_planes(K, bwd) + (uv ? 2 * K : 0);
     if (lane == 0) mbar_expect_tx(bar, bytes * (uint32_t)np);
     __syncwarp();
     for (int p = lane; p < np; p += 32) {
@@ -69,7 +71,8 @@ __device__ __forceinline__ void issue_tile_n(float* stage, uint64_t* bar, const 
         else if (p < 10 + 4 * K) src = a.lamb + (b * K + (p - 10 - 3 * K)) * plane;
         else if (p < 10 + 7 * K) src = a.weight + (b * 3 * K + (p - 10 - 4 * K)) * plane;
         else if (p < 13 + 7 * K) src = a.g_diff + (b * 3 + (p - 10 - 7 * K)) * plane;
-        else src = a.g_spec + (b * 3 + (p - 13 - 7 * K)) * plane;
+        else if (p < 16 + 7 * K) src = a.g_spec + (b * 3 + (p - 13 - 7 * K)) * plane;
+        else src = a.lobe_uv_in + (b * 2 * K + (p - 16 - 7 * K)) * plane;
         bulk_g2s(stage + (size_t)p * PT, src + pix0, bytes, bar);
     }
 }
@@ -86,6 +89,7 @@ __device__ __forceinline__ RenderSgArgs stage_view_n(const RenderSgArgs& a, floa
     s.weight = stage + (10 + 4 * K) * PT;
     s.g_diff = stage + (10 + 7 * K) * PT;
     s.g_spec = stage + (13 + 7 * K) * PT;
+    s.lobe_uv_in = stage + (16 + 7 * K) * PT;
     return s;
 }
 
@@ -166,6 +170,17 @@ __device__ __forceinline__ bool group_tile_fwd(const RenderSgArgs& a, const Rend
         upk(U2[i], U[2 * i], U[2 * i + 1]);
         upk(V2[i], V[2 * i], V[2 * i + 1]);
     }
+    if (a.lobe_uv_out && active) {   // the backward's U_k, V_k (regular pixels; the others recompute them in the general path)
+#pragma unroll
+        for (int k = 0; k < kLPT; ++k) {
+            const int kk = h * kLPT + k;
+            if (kk < sv.K) {
+                float* o = a.lobe_uv_out + (vo.b * (2 * sv.K) + 2 * kk) * vo.plane + vo.pix;
+                o[0] = U[k];
+                o[vo.plane] = V[k];
+            }
+        }
+    }
     float Dc[3] = {0.f, 0.f, 0.f}, Sc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < kLPT; ++k) {
@@ -195,7 +210,7 @@ __device__ __forceinline__ bool group_tile_fwd(const RenderSgArgs& a, const Rend
 }
 
 // ---- one tile, backward ---------------------------------------------------------------------
-template <int TPP, bool PIX, bool LOBE>
+template <int TPP, bool PIX, bool LOBE, bool SAVED>
 __device__ __forceinline__ bool group_tile_bwd(const RenderSgArgs& a, const RenderSgArgs& sv, const EnvTab& tab, const TabS& ts,
                                                const PixView& vi, const PixView& vo, bool in_range, int h) {
     const int lane = threadIdx.x & 31, lane_base = lane - h;
@@ -286,7 +301,7 @@ __device__ __forceinline__ bool group_tile_bwd(const RenderSgArgs& a, const Rend
                     const int d = m + half * TPP + j;
                     const float wx = tab.lx[d], wy = tab.ly[d], wz = tab.lz[d];
                     part[half * TPP + j] =
-                        lobes_bwd_acc_pk<kLPT, PIX, LOBE>(g2, P2, Q2, arg[j], e[j], wx, wy, wz, tab.w[d] * wz, spec[j]);
+                        lobes_bwd_acc_pk<kLPT, PIX, LOBE, SAVED>(g2, P2, Q2, arg[j], e[j], wx, wy, wz, tab.w[d] * wz, spec[j]);
                 }
             }
             // next pair (clamped on the last trip: recomputes the last pair, result unused)
@@ -338,7 +353,7 @@ __device__ __forceinline__ bool group_tile_bwd(const RenderSgArgs& a, const Rend
                     const int d = m + half * TPP + j;
                     const float wx = tab.lx[d], wy = tab.ly[d], wz = tab.lz[d];
                     part[half * TPP + j] =
-                        lobes_bwd_acc_pk<kLPT, PIX, LOBE>(g2, P2, Q2, arg[j], e[j], wx, wy, wz, tab.w[d] * wz, spec[j]);
+                        lobes_bwd_acc_pk<kLPT, PIX, LOBE, SAVED>(g2, P2, Q2, arg[j], e[j], wx, wy, wz, tab.w[d] * wz, spec[j]);
                 }
             }
             if (PIX) {
@@ -357,6 +372,15 @@ __device__ __forceinline__ bool group_tile_bwd(const RenderSgArgs& a, const Rend
 #endif
         pixel_gradl2_fold(gl, gl2);
         gradspk_unpack<kLPT>(lg, g2);
+        if (SAVED) {   // U_k, V_k of the forward pass, staged with the tile
+#pragma unroll
+            for (int k = 0; k < kLPT; ++k) {
+                const int kk = h * kLPT + k;
+                const bool okk = kk < sv.K;
+                lg.U[k] = okk ? sv.lobe_uv_in[(size_t)(2 * kk) * vi.plane + vi.pix] : 0.f;
+                lg.V[k] = okk ? sv.lobe_uv_in[(size_t)(2 * kk + 1) * vi.plane + vi.pix] : 0.f;
+            }
+        }
     }
     // epilogue: outputs are predicated per thread by nulling the pointers of inactive threads
     RenderSgArgs ao = a;
@@ -434,7 +458,7 @@ __device__ __noinline__ void group_general_pixel(const RenderSgArgs& a, const En
 }
 
 // MODE 0 forward, 1 backward
-template <int MODE, int TPP, bool PIX, bool LOBE, int MINB>
+template <int MODE, int TPP, bool PIX, bool LOBE, int MINB, bool SAVED = false>
 __global__ void __launch_bounds__(kThreads, MINB) render_sg_group_kernel(const __grid_constant__ RenderSgArgs a, const __grid_constant__ EnvTab tab,
                                                                           const __grid_constant__ TileMaps maps,
                                                                           const unsigned total_tiles, const unsigned tiles_per_img) {
@@ -443,7 +467,7 @@ __global__ void __launch_bounds__(kThreads, MINB) render_sg_group_kernel(const _
     __shared__ TabS ts;
     constexpr bool BWD = (MODE == 1);
     constexpr int PT = kThreads / TPP;
-    const int np = stage_planes(a.K, BWD);
+    const int np = stage_planes(a.K, BWD) + (SAVED ? 2 * a.K : 0);
     float* const stage0 = reinterpret_cast<float*>(smem_raw);
     float* const stage1 = stage0 + (size_t)np * PT;
     for (int i = threadIdx.x; i < IRB_MAX_DIRS; i += kThreads) {
@@ -466,7 +490,7 @@ __global__ void __launch_bounds__(kThreads, MINB) render_sg_group_kernel(const _
     const size_t plane = (size_t)a.R * a.C;
     const int q = threadIdx.x / TPP, h = threadIdx.x % TPP;
     unsigned t = blockIdx.x;
-    if (t < total_tiles && threadIdx.x < 32) issue_tile_n(stage0, &full_bar[0], a, maps, t, tiles_per_img, BWD, PT);
+    if (t < total_tiles && threadIdx.x < 32) issue_tile_n(stage0, &full_bar[0], a, maps, t, tiles_per_img, BWD, PT, SAVED);
     for (unsigned it = 0; t < total_tiles; ++it, t += gridDim.x) {
         const int s = it & 1;
         float* const cur = s ? stage1 : stage0;
@@ -475,7 +499,7 @@ __global__ void __launch_bounds__(kThreads, MINB) render_sg_group_kernel(const _
             const unsigned kfill = (it + 1) >> 1;            // fill index of stage s^1
             if (kfill >= 1) mbar_wait(&empty_bar[s ^ 1], (kfill - 1) & 1);   // everyone finished the previous tenant
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue_tile_n(s ? stage0 : stage1, &full_bar[s ^ 1], a, maps, tn, tiles_per_img, BWD, PT);
+            issue_tile_n(s ? stage0 : stage1, &full_bar[s ^ 1], a, maps, tn, tiles_per_img, BWD, PT, SAVED);
         }
         mbar_wait(&full_bar[s], (it >> 1) & 1);
         const size_t b = t / tiles_per_img, pix0 = (size_t)(t % tiles_per_img) * PT;
@@ -485,7 +509,7 @@ __global__ void __launch_bounds__(kThreads, MINB) render_sg_group_kernel(const _
         const PixView vo{b, pix0 + q, plane};
         bool irr;
         if (MODE == 0) irr = group_tile_fwd<TPP>(a, sv, tab, ts, vi, vo, in_range, h);
-        else irr = group_tile_bwd<TPP, PIX, LOBE>(a, sv, tab, ts, vi, vo, in_range, h);
+        else irr = group_tile_bwd<TPP, PIX, LOBE, SAVED>(a, sv, tab, ts, vi, vo, in_range, h);
         mbar_arrive(&empty_bar[s]);   // this thread is done with stage s
         unsigned m = __ballot_sync(0xffffffffu, irr && h == 0);
         while (m) {   // rare: the whole warp shades each such pixel through the general path

@@ -8,7 +8,7 @@ namespace irb {
 
 // Tensor maps of the planes a tile stages, in stage order.  on = 0: descriptors unavailable, kernels fall back to one
 // cp.async.bulk per plane.
-constexpr int kMaxTileMaps = 9;
+constexpr int kMaxTileMaps = 10;
 struct TileMaps {
     CUtensorMap m[kMaxTileMaps];
     int on;

@@ -24,6 +24,8 @@ from ._lazy import LazyTensor, unlazy
 __all__ = ['output2env', 'renderingLayer', 'LSregress', 'LSregressDiffSpec', 'renderLoss', 'renderLossTerms']
 
 
+# A/B and test knob: False makes the fused backward rebuild U_k / V_k itself (no side tensor from the forward)
+_SAVE_LOBE_SUMS = True
 # measurement hook: a list that receives ('render_sg_bwd', start_event, end_event) per fused backward launch (bench.py)
 _EVENT_SINK = None
 
@@ -253,12 +255,18 @@ class _RenderSG(torch.autograd.Function):
         dev = axis.device
         od = torch.empty(B, 3, R, C, device=dev, dtype=torch.float32)
         os_ = torch.empty_like(od)
+        # the per-lobe hemisphere sums U_k, V_k: written by the forward when a lobe-side gradient will be asked for, so that
+        # the backward does not rebuild them (96 B/pixel at K = 12 on a path that uses 7 % of the HBM bandwidth)
+        need = ctx.needs_input_grad
+        uv = (torch.empty(B, 2 * K, R, C, device=dev, dtype=torch.float32)
+              if (_SAVE_LOBE_SUMS and (need[0] or any(need[3:6]))) else None)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().irb_render_sg_fwd(
                 _lib.ptr(albedo), _lib.ptr(normal), _lib.ptr(rough), _lib.ptr(axis), _lib.ptr(lamb),
-                _lib.ptr(weight), _lib.ptr(view), _lib.ptr(od), _lib.ptr(os_), B, K, R, C, envH, envW, float(F0),
-                int(warp), _lib.stream_ptr(dev)), 'irb_render_sg_fwd')
+                _lib.ptr(weight), _lib.ptr(view), _lib.ptr(od), _lib.ptr(os_), _lib.ptr(uv), B, K, R, C, envH, envW,
+                float(F0), int(warp), _lib.stream_ptr(dev)), 'irb_render_sg_fwd')
         ctx.save_for_backward(albedo, normal, rough, axis, lamb, weight, view)
+        ctx.uv = uv
         ctx.cfg = (float(F0), envH, envW, int(warp))
         return od, os_
 
@@ -280,8 +288,8 @@ class _RenderSG(torch.autograd.Function):
                 e0.record()
             _lib.check(_lib.lib().irb_render_sg_bwd(
                 _lib.ptr(albedo), _lib.ptr(normal), _lib.ptr(rough), _lib.ptr(axis), _lib.ptr(lamb),
-                _lib.ptr(weight), _lib.ptr(view), _lib.ptr(g_d), _lib.ptr(g_s), *[_lib.ptr(o) for o in outs],
-                B, K, R, C, envH, envW, F0, warp, _lib.stream_ptr(dev)), 'irb_render_sg_bwd')
+                _lib.ptr(weight), _lib.ptr(view), _lib.ptr(g_d), _lib.ptr(g_s), _lib.ptr(ctx.uv),
+                *[_lib.ptr(o) for o in outs], B, K, R, C, envH, envW, F0, warp, _lib.stream_ptr(dev)), 'irb_render_sg_bwd')
             if sink is not None:
                 e1.record()
                 sink.append(('render_sg_bwd', e0, e1))

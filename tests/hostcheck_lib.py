@@ -23,7 +23,7 @@ class EnvTab(C.Structure):
 class RenderSgArgs(C.Structure):
     _fields_ = [(n, FP) for n in ('albedo', 'normal', 'rough', 'axis', 'lamb', 'weight', 'view', 'out_diff',
                                   'out_spec', 'g_diff', 'g_spec', 'g_albedo', 'g_normal', 'g_rough', 'g_axis',
-                                  'g_lamb', 'g_weight')] + \
+                                  'g_lamb', 'g_weight', 'lobe_uv_out', 'lobe_uv_in')] + \
                [('B', C.c_int), ('K', C.c_int), ('R', C.c_int), ('C', C.c_int), ('F0', C.c_float), ('warp', C.c_int)]
 
 

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(built):
     from inverserenderingofindoorscene_b200 import _lib
     assert sorted(_lib.SIGNATURES) == declared
     h = _lib.lib()
-    assert h.irb_abi_version() == 1
+    assert h.irb_abi_version() == 2
 
 
 def test_sass_is_sm100a_only(built):

@@ -53,7 +53,7 @@ def test_fused_render_math(lib, path, dbl):
     g_ax, g_lam, g_wt = np.zeros_like(axis), np.zeros_like(lamb), np.zeros_like(weight)
     a = hc.RenderSgArgs(hc.p(alb), hc.p(nrm), hc.p(rg), hc.p(axis), hc.p(lamb), hc.p(weight), hc.p(view),
                         hc.p(od), hc.p(os_), hc.p(z['gD']), hc.p(z['gS']), hc.p(g_alb), hc.p(g_nrm), hc.p(g_rg),
-                        hc.p(g_ax), hc.p(g_lam), hc.p(g_wt), B, K, R, Cc, 0.05, 1)
+                        hc.p(g_ax), hc.p(g_lam), hc.p(g_wt), None, None, B, K, R, Cc, 0.05, 1)
     assert lib.hc_render_sg_fwd(dbl, C.byref(a), C.byref(tab)) == 0
     assert lib.hc_render_sg_bwd(dbl, C.byref(a), C.byref(tab)) == 0
     # double instantiation: only the fp32 rounding of the pooled inputs / stored outputs remains.
@@ -156,7 +156,7 @@ def test_edge_cases_math(lib, dbl):
     gDn, gSn = gD.numpy(), gS.numpy()
     a = hc.RenderSgArgs(hc.p(arrs[0]), hc.p(arrs[1]), hc.p(arrs[2]), hc.p(arrs[3]), hc.p(arrs[4]), hc.p(arrs[5]),
                         hc.p(view), hc.p(od), hc.p(os_), hc.p(gDn), hc.p(gSn), *[hc.p(o) for o in outs],
-                        B, K, R, Cc, 0.05, 1)
+                        None, None, B, K, R, Cc, 0.05, 1)
     assert lib.hc_render_sg_fwd(dbl, C.byref(a), C.byref(tab)) == 0
     assert lib.hc_render_sg_bwd(dbl, C.byref(a), C.byref(tab)) == 0
     tol = 2e-6 if dbl else 5e-4
@@ -189,7 +189,7 @@ def test_warp_cooperative_general_path(lib, path):
         od, os_, g_alb, g_nrm, g_rg, g_ax, g_lam, g_wt = outs
         a = hc.RenderSgArgs(hc.p(alb), hc.p(nrm), hc.p(rg), hc.p(axis), hc.p(lamb), hc.p(weight), hc.p(view),
                             hc.p(od), hc.p(os_), hc.p(z['gD']), hc.p(z['gS']), hc.p(g_alb), hc.p(g_nrm), hc.p(g_rg),
-                            hc.p(g_ax), hc.p(g_lam), hc.p(g_wt), B, K, R, Cc, 0.05, 1)
+                            hc.p(g_ax), hc.p(g_lam), hc.p(g_wt), None, None, B, K, R, Cc, 0.05, 1)
         assert fwd(C.byref(a), C.byref(tab)) == 0
         assert bwd(C.byref(a), C.byref(tab)) == 0
         return outs

@@ -523,3 +523,36 @@ def test_pred_to_shading(irb):
         u.predToShading(pred, SGNum=K)          # CPU tensor: no CPU path
     with pytest.raises(ValueError):
         u.predToShading(pred.numpy(), SGNum=K)  # NumPy batch of 2: the reference squeezes a batch of one
+
+
+@pytest.mark.parametrize('K', [5, 12, 24])
+def test_saved_lobe_sums_match_recompute(irb, K):
+    """the forward's side tensor of per-lobe hemisphere sums (U_k, V_k; ABI 2) against a backward that rebuilds them:
+    same gradients (the two paths share every other instruction), incl. irregular pixels and partial tiles / tails"""
+    from oracle import render_oracle as ro
+    B, R, C = 2, 13, 20          # plane = 260: partial last tile
+    ins64 = ro.synth_inputs(B, R, C, R, C, K, seed=900 + K, dtype=torch.float64, hi=0.95)
+    ins64[1][0, :, 0, 0] = torch.tensor([0.0, 0.0, 0.0])
+    ins64[1][1, :, 3, 5] = torch.tensor([0.2, 0.1, 1.3])
+    dev = torch.device('cuda')
+    g = torch.Generator().manual_seed(K)
+    gD, gS = torch.rand(B, 3, R, C, generator=g).to(dev), torch.rand(B, 3, R, C, generator=g).to(dev)
+    rl = irb.renderingLayer(imWidth=C, imHeight=R, isCuda=True)
+    res = []
+    for save in (True, False):
+        irb._SAVE_LOBE_SUMS = save
+        try:
+            ins = [t.float().to(dev).requires_grad_(True) for t in ins64]
+            d, s = rl.forwardSG(*ins)
+            res.append([d.detach(), s.detach()] + list(torch.autograd.grad([d, s], ins, [gD, gS])))
+        finally:
+            irb._SAVE_LOBE_SUMS = True
+    for a, b, name in zip(res[0], res[1], RENDER_NAMES):
+        assert relerr(a.cpu().numpy(), b.cpu().numpy()) <= 2e-6, name
+    # SG-side gradients only (the trainLight pattern: LOBE-only backward kernel) with the side tensor
+    ins = [t.float().to(dev) for t in ins64]
+    sg = [t.clone().requires_grad_(True) for t in ins[3:]]
+    d, s = rl.forwardSG(ins[0], ins[1], ins[2], *sg)
+    gg = torch.autograd.grad([d, s], sg, [gD, gS])
+    for a, b, name in zip(gg, res[1][5:], RENDER_NAMES[5:]):
+        assert relerr(a.cpu().numpy(), b.cpu().numpy()) <= 2e-6, name
