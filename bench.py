@@ -180,7 +180,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     val = rows * W * args.steps / dt / 1e6
     sample = _cpu_sample_text(kind, rows, threads)
-    print(json.dumps({
+    emit(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': val,
         'unit': 'Mpix/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -566,7 +566,7 @@ def run_ours(args):
         elif world > 1:
             line['cpu_baseline'] = {'value': None, 'unit': 'Mpix/s', 'cores': os.cpu_count(), 'kind': 'reference',
                                     'sample': 'reported at N=1 only'}
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -585,14 +585,48 @@ def run_profile(args):
     sys.exit(rc)
 
 
+class StdoutToStderr(object):
+    """the contract is ONE JSON line on stdout: anything a library prints meanwhile (NCCL's version banner under
+    NCCL_DEBUG=VERSION, warnings of a C extension) is routed to stderr at the file-descriptor level; `emit` writes the line"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.saved, (text + '\n').encode())
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+OUT = None
+
+
+def emit(text):
+    if OUT is not None:
+        OUT.emit(text)
+    else:
+        print(text, flush=True)
+
+
 def main():
+    global OUT
     args = parse()
     if args.profile:
         run_profile(args)
-    if args.impl == 'reference':
-        run_reference(args)
-    else:
-        run_ours(args)
+    with StdoutToStderr() as OUT:
+        if args.impl == 'reference':
+            run_reference(args)
+        else:
+            run_ours(args)
+    OUT = None
 
 
 if __name__ == '__main__':

@@ -346,6 +346,42 @@ def run_bilateral_mode0(BL, dev, iters=5):
             'hbm_frac_of_model': model_bytes / (fb * 1e-3) / 1e9 / peak_hbm()}
 
 
+def run_ctor_cost(models):
+    """testReal.py:341-346 builds a renderingLayer per image with that image's (H, W, fov): first construction of a geometry
+    (host arithmetic + 5 H2D copies) against a repeat (table cache hit)"""
+    import time
+    res = {}
+    for tag, (w, h, fov) in (('160x120_fov57', (160, 120, 57)), ('213x120_fov57', (213, 120, 57)), ('160x90_fov42.75', (160, 90, 42.75))):
+        models._LAYER_TABLES.clear()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        models.renderingLayer(imWidth=w, imHeight=h, fov=fov, isCuda=True)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        models.renderingLayer(imWidth=w, imHeight=h, fov=fov, isCuda=True)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        res[tag] = {'first_ms': (t1 - t0) * 1e3, 'cached_ms': (t2 - t1) * 1e3}
+    return res
+
+
+def graphed_step_ms(step, timed_ranks, dev, world):
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        step()
+    torch.cuda.synchronize()
+    ms = timed_ranks(g.replay, 20, 3, dev, world)
+    del g
+    return {'ms_per_step': ms, 'note': 'torch.cuda.CUDAGraph capture of the whole step (forward, loss, all-reduce, backward), replay timed'}
+
+
 def extras_for_bench(models, sharding, dev, rank, world, timed_ranks, make_render_step):
     """secondary BASELINE configs for the bench line (`extras`): device-timed, max over ranks, a handful of steps each"""
     from inverserenderingofindoorscene_b200 import BilateralLayer as BL
@@ -367,9 +403,17 @@ def extras_for_bench(models, sharding, dev, rank, world, timed_ranks, make_rende
                              'render-loss step (output2env -> forwardEnv -> render loss -> all-reduce -> backward to the SG '
                              'parameters); the LightNet CNNs are out of scope' % (b, b * world),
                      'ms_per_step': ms, 'images_per_s': b * world / ms * 1e3}
+        if name == 'config3_strong':
+            # small per-GPU batches are launch / host bound (6 kernels + ~25 tiny torch ops per step): the same step captured
+            # once in a CUDA graph (the library neither allocates nor synchronises, so its launches are capturable) and replayed
+            try:
+                out[name]['cuda_graph'] = graphed_step_ms(st, timed_ranks, dev, world)
+            except Exception as ex:
+                out[name]['cuda_graph'] = {'error': repr(ex)[:200]}
         del st
     torch.cuda.empty_cache()
     if world == 1:
+        out['layer_construction'] = run_ctor_cost(models)
         out['config4_bilateral'] = run_bilateral_mode0(BL, dev)
         torch.cuda.empty_cache()
         out['reference_torch_cuda'] = run_reference_torch_cuda(dev)

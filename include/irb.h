@@ -211,6 +211,10 @@ int irb_bg_bistochastization(const void* ws, double* n, double* m, int B, int H,
 /* per image: number of vertices V (device int[B]) and of directed neighbour links E (device uint64[B]) -- SURVEY 8d */
 int irb_bg_stats(const void* ws, int* nverts, unsigned long long* nlinks, int B, int H, int W, void* stream);
 
+/* per image (device int[B]): 1 if some pixel's grid coordinate left [0, 255) when the grid was built -- i.e. guide *
+ * guide_scale outside [0, 255] (or sigma too small for the image size).  The reference's hash (BilateralGrid.py:57,86-88)
+ * aliases there; this library then gives unspecified vertex ids.  The build itself never synchronises to report it. */
+int irb_bg_range_flags(const void* ws, int* flags, int B, int H, int W, void* stream);
 /* test / debugging aid: PCG scalars {rho, <p,q>, <r,r>, -} per (image, channel, iteration) of the last solve on this
  * workspace, device fp64 [B][4][258][4]; slot 257 = {<b,b>, -, -, -} */
 int irb_bg_debug_scalars(const void* ws, double* out, int B, int ch, int H, int W, void* stream);

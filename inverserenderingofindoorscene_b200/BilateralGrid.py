@@ -108,6 +108,16 @@ class BilateralGrid(object):
         return n[:V].cpu().numpy(), m[:V].cpu().numpy()
 
     @property
+    def range_ok(self):
+        """False if a grid coordinate left [0, 255): the guide was not in [0, 255] (the reference's hash requirement)"""
+        ws, _ = self._build(1)
+        fl = torch.empty(1, dtype=torch.int32, device=self._dev)
+        with torch.cuda.device(self._dev):
+            _lib.check(_lib.lib().irb_bg_range_flags(_lib.ptr(ws), _lib.ptr(fl), 1, self.H, self.W, _lib.stream_ptr(self._dev)),
+                       'irb_bg_range_flags')
+        return int(fl.item()) == 0
+
+    @property
     def nlinks(self):
         ws, _ = self._build(1)
         nv = torch.empty(1, dtype=torch.int32, device=self._dev)

@@ -26,6 +26,10 @@ from . import _lib
 REQUIRES_CONF_GRAD = True   # BilateralLayer.py:17
 _POISON = int(os.environ['IRB_DEBUG_POISON'], 0) if os.environ.get('IRB_DEBUG_POISON') else None
 CG_MAXITER_OVERRIDE = None  # int to force the PCG iteration count
+# Legacy behaviour switch: the reference passes cg_tol (1e-5) where SciPy expects maxiter (BilateralLayer.py:44,79).
+# Fortran-era SciPy is believed to have truncated that to 0 and iterated until the tolerance was met; set this to True to
+# reproduce THAT pipeline (iterate to cg_tol, capped at the library's 256 iterations) instead of the intended 10-12 iterations.
+CG_LEGACY_CONVERGE = False
 
 
 def _chk(t, name, shape_tail=None):
@@ -57,6 +61,8 @@ def _solver_params(grid_params_arr, bs_params_arr):
     gp = _host_values(grid_params_arr)
     bp = _host_values(bs_params_arr)
     maxiter = int(round(bp[3])) if CG_MAXITER_OVERRIDE is None else int(CG_MAXITER_OVERRIDE)
+    if CG_LEGACY_CONVERGE and CG_MAXITER_OVERRIDE is None:
+        maxiter = 256
     return gp[0], gp[1], gp[2], bp[0], bp[1], bp[2], maxiter
 
 

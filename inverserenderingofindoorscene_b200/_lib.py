@@ -42,6 +42,7 @@ SIGNATURES = {
     'irb_bg_apply': [_P, _I, _P, _P, _I, _I, _I, _I, _P],
     'irb_bg_bistochastization': [_P, _P, _P, _I, _I, _I, _P],
     'irb_bg_stats': [_P, _P, _P, _I, _I, _I, _P],
+    'irb_bg_range_flags': [_P, _P, _I, _I, _I, _P],
     'irb_bg_debug_scalars': [_P, _P, _I, _I, _I, _I, _P],
     'irb_bg_solve_fwd': [_P, _P, _P, _I, _I, _I, _I, _D, _D, _D, _I, _P, _P, _P],
     'irb_bg_solve_bwd': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _D, _D, _D, _I, _P, _P, _P],

@@ -26,7 +26,7 @@ constexpr int BG_MAX_CH = 4;
 struct BgLayout {
     int B, H, W, ch;
     size_t P;
-    size_t hdr, idx, vstart, ukeys, nbr, n0, n1, m, m0, keysA, keysB, payA, payB, hist, dtot;
+    size_t hdr, oor, idx, vstart, ukeys, nbr, n0, n1, m, m0, keysA, keysB, payA, payB, hist, dtot;
     size_t wsplat, minv, bvec, r, p0, p1, q, sol, np, scal, total;
 };
 
@@ -40,6 +40,7 @@ static BgLayout make_layout(int B, int H, int W, int ch) {
     size_t o = 0;
     auto take = [&](size_t bytes) { const size_t r = o; o = align_up(o + bytes); return r; };
     L.hdr = take(sizeof(int) * Bz);
+    L.oor = take(sizeof(int) * Bz);   // per image: 1 if a grid coordinate left [0, 255) (hash aliasing; see irb_bg_range_flags)
     L.idx = take(4 * P * Bz);
     L.vstart = take(4 * (P + 1) * Bz);
     L.ukeys = take(8 * P * Bz);
@@ -95,6 +96,9 @@ __global__ void bg_keys_kernel(const float* __restrict__ guide, float gscale, vo
     const long long cl = (long long)(Y / sl), cu = (long long)(U / sc), cv = (long long)(V / sc);
     // sum_i coord_i * 255^i  (exact in the reference's fp64 too)
     const long long key = cx + 255LL * (cy + 255LL * (cl + 255LL * (cu + 255LL * cv)));
+    // the reference's hash needs every coordinate in [0, 255) (guide * scale in [0, 255]); outside it the hash aliases and --
+    // with the 40-bit sort chosen from the sigma bounds -- vertex ids are no longer np.unique's.  Flag it.
+    if ((cx | cy | cl | cu | cv) < 0 || cx >= 255 || cy >= 255 || cl >= 255 || cu >= 255 || cv >= 255) at<int>(ws, L.oor)[b] = 1;
     at<unsigned long long>(ws, L.keysA)[t] = (unsigned long long)key;
     at<int>(ws, L.payA)[t] = (int)p;
 }
@@ -749,6 +753,7 @@ extern "C" int irb_bg_build(const float* guide, float guide_scale, int B, int H,
     }
     cudaStream_t st = (cudaStream_t)stream;
     const size_t tot = L.P * (size_t)B;
+    cudaMemsetAsync(at<int>(ws, L.oor), 0, sizeof(int) * (size_t)B, st);
     bg_keys_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(guide, guide_scale, ws, L, sigma_luma, sigma_chroma, sigma_spatial);
     // hash < 255^5 < 2^40 whenever every coordinate is < 255 (the reference's own requirement); otherwise
     // sort all 64 bits so that aliasing hashes are still ordered exactly like np.unique orders them
@@ -874,6 +879,18 @@ extern "C" int irb_bg_debug_scalars(const void* ws, double* out, int B, int ch, 
                                           cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
     if (e != cudaSuccess) {
         set_error("bg_debug_scalars: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+extern "C" int irb_bg_range_flags(const void* ws, int* flags, int B, int H, int W, void* stream) {
+    if (int rc = bg_check(ws, B, H, W, 1, "bg_range_flags")) return rc;
+    IRB_REQUIRE(flags != nullptr, "bg_range_flags: null output");
+    const BgLayout L = make_layout(B, H, W, 1);
+    const cudaError_t e = cudaMemcpyAsync(flags, at<int>(ws, L.oor), 4 * (size_t)B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        set_error("bg_range_flags: %s", cudaGetErrorString(e));
         return (int)e;
     }
     return 0;

@@ -283,9 +283,13 @@ extern "C" int irb_render_sg_fwd(const float* albedo, const float* normal, const
     if (variant == 0) {
         int rc;
         const char* w = "render_sg_fwd(group)";
-        if (K <= 6) rc = launch_group(render_sg_group_kernel<0, 1, false, false, 4>, a, tab, false, st, w, kThreads / 1);
-        else if (K <= 12) rc = launch_group(render_sg_group_kernel<0, 2, false, false, 4>, a, tab, false, st, w, kThreads / 2);
-        else rc = launch_group(render_sg_group_kernel<0, 4, false, false, 4>, a, tab, false, st, w, kThreads / 4);
+#define IRB_GROUP_FWD(TPP)                                                                                                   \
+    (K == TPP * kLPT ? launch_group(render_sg_group_kernel<0, TPP, false, false, 4, false, true>, a, tab, false, st, w, kThreads / TPP) \
+                     : launch_group(render_sg_group_kernel<0, TPP, false, false, 4>, a, tab, false, st, w, kThreads / TPP))
+        if (K <= 6) rc = IRB_GROUP_FWD(1);
+        else if (K <= 12) rc = IRB_GROUP_FWD(2);
+        else rc = IRB_GROUP_FWD(4);
+#undef IRB_GROUP_FWD
         return rc;   // pixels outside the regular regime were shaded inside the kernel (group_general_pixel)
     }
     const dim3 grid((unsigned)(((size_t)R * C + kThreads - 1) / kThreads), (unsigned)B);
@@ -327,25 +331,21 @@ extern "C" int irb_render_sg_bwd(const float* albedo, const float* normal, const
     if (variant == 0) {
         int rc;
         const char* w = "render_sg_bwd(group)";
-        const char* mb = getenv("IRB_BWD_MINB");  // A/B knob: resident CTAs the full backward is compiled for (2: 255 regs, 3: 168, 4: 128)
-        const int minb = (mb && mb[0] >= '2' && mb[0] <= '4') ? mb[0] - '0' : 2;
         // saved: U_k / V_k of the forward pass are staged with the tile (16-byte alignment like every staged plane)
         const bool saved = lobe && a.lobe_uv_in != nullptr && (((uintptr_t)a.lobe_uv_in & 15u) == 0);
         if (!saved) a.lobe_uv_in = nullptr;
-#define IRB_GROUP_BWD(TPP)                                                                                                   \
-    (pix && lobe                                                                                                             \
-         ? (saved ? (minb == 4   ? launch_group(render_sg_group_kernel<1, TPP, true, true, 4, true>, a, tab, true, st, w, kThreads / TPP, true) \
-                     : minb == 3 ? launch_group(render_sg_group_kernel<1, TPP, true, true, 3, true>, a, tab, true, st, w, kThreads / TPP, true) \
-                                 : launch_group(render_sg_group_kernel<1, TPP, true, true, 2, true>, a, tab, true, st, w, kThreads / TPP, true)) \
-                  : (minb == 4   ? launch_group(render_sg_group_kernel<1, TPP, true, true, 4>, a, tab, true, st, w, kThreads / TPP) \
-                     : minb == 3 ? launch_group(render_sg_group_kernel<1, TPP, true, true, 3>, a, tab, true, st, w, kThreads / TPP) \
-                                 : launch_group(render_sg_group_kernel<1, TPP, true, true, 2>, a, tab, true, st, w, kThreads / TPP))) \
-     : pix ? launch_group(render_sg_group_kernel<1, TPP, true, false, 3>, a, tab, true, st, w, kThreads / TPP)               \
-           : (saved ? launch_group(render_sg_group_kernel<1, TPP, false, true, 3, true>, a, tab, true, st, w, kThreads / TPP, true) \
-                    : launch_group(render_sg_group_kernel<1, TPP, false, true, 3>, a, tab, true, st, w, kThreads / TPP)))
+        // kernel = <1, TPP, PIX, LOBE, resident CTAs (2: 255 registers for the full backward, 3 otherwise), SAVED, FULLK>
+#define IRB_BWD_K(TPP, PIXV, LOBEV, MINBV, SAVEDV)                                                                                   \
+    (K == TPP * kLPT ? launch_group(render_sg_group_kernel<1, TPP, PIXV, LOBEV, MINBV, SAVEDV, true>, a, tab, true, st, w, kThreads / TPP, SAVEDV) \
+                     : launch_group(render_sg_group_kernel<1, TPP, PIXV, LOBEV, MINBV, SAVEDV, false>, a, tab, true, st, w, kThreads / TPP, SAVEDV))
+#define IRB_GROUP_BWD(TPP)                                                                                              \
+    (pix && lobe ? (saved ? IRB_BWD_K(TPP, true, true, 2, true) : IRB_BWD_K(TPP, true, true, 2, false))                  \
+     : pix       ? IRB_BWD_K(TPP, true, false, 3, false)                                                                 \
+                 : (saved ? IRB_BWD_K(TPP, false, true, 3, true) : IRB_BWD_K(TPP, false, true, 3, false)))
         if (K <= 6) rc = IRB_GROUP_BWD(1);
         else if (K <= 12) rc = IRB_GROUP_BWD(2);
         else rc = IRB_GROUP_BWD(4);
+#undef IRB_BWD_K
 #undef IRB_GROUP_BWD
         return rc;   // pixels outside the regular regime were handled inside the kernel (group_general_pixel)
     }

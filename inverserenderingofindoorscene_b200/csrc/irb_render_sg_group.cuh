@@ -458,7 +458,9 @@ __device__ __noinline__ void group_general_pixel(const RenderSgArgs& a, const En
 }
 
 // MODE 0 forward, 1 backward
-template <int MODE, int TPP, bool PIX, bool LOBE, int MINB, bool SAVED = false>
+// FULLK: K == TPP * kLPT exactly (6 / 12 / 24 lobes): the per-lobe `kk < K` guards, the padding lobes and the runtime-K address
+// arithmetic of the once-per-pixel prologue / epilogue fold away (that code is ~20 % of the instructions a tile executes)
+template <int MODE, int TPP, bool PIX, bool LOBE, int MINB, bool SAVED = false, bool FULLK = false>
 __global__ void __launch_bounds__(kThreads, MINB) render_sg_group_kernel(const __grid_constant__ RenderSgArgs a, const __grid_constant__ EnvTab tab,
                                                                           const __grid_constant__ TileMaps maps,
                                                                           const unsigned total_tiles, const unsigned tiles_per_img) {
@@ -504,12 +506,14 @@ __global__ void __launch_bounds__(kThreads, MINB) render_sg_group_kernel(const _
         mbar_wait(&full_bar[s], (it >> 1) & 1);
         const size_t b = t / tiles_per_img, pix0 = (size_t)(t % tiles_per_img) * PT;
         const bool in_range = pix0 + q < plane;
-        const RenderSgArgs sv = stage_view_n(a, cur, PT);
+        RenderSgArgs sv = stage_view_n(a, cur, PT);
+        RenderSgArgs ak = a;
+        if (FULLK) ak.K = sv.K = TPP * kLPT;   // compile-time lobe count
         const PixView vi{0, (size_t)q, (size_t)PT};
         const PixView vo{b, pix0 + q, plane};
         bool irr;
-        if (MODE == 0) irr = group_tile_fwd<TPP>(a, sv, tab, ts, vi, vo, in_range, h);
-        else irr = group_tile_bwd<TPP, PIX, LOBE, SAVED>(a, sv, tab, ts, vi, vo, in_range, h);
+        if (MODE == 0) irr = group_tile_fwd<TPP>(ak, sv, tab, ts, vi, vo, in_range, h);
+        else irr = group_tile_bwd<TPP, PIX, LOBE, SAVED>(ak, sv, tab, ts, vi, vo, in_range, h);
         mbar_arrive(&empty_bar[s]);   // this thread is done with stage s
         unsigned m = __ballot_sync(0xffffffffu, irr && h == 0);
         while (m) {   // rare: the whole warp shades each such pixel through the general path

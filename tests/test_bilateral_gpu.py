@@ -170,3 +170,28 @@ def test_grid_facade_operators(mods):
                                x.astype(np.float32).astype(np.float64))
     assert gc.shape == gcr.shape == (H * W, 3)
     assert relerr(gt, gtr) <= 1e-5 and relerr(gc, gcr) <= 1e-5
+
+
+def test_range_flag_and_legacy_convergence(mods):
+    """guide outside [0, 255] is flagged; CG_LEGACY_CONVERGE iterates to the tolerance like the oracle does"""
+    from oracle import bilateral_oracle as bo
+    BL, BG = mods
+    H, W = 48, 64
+    guide = bo.synth_guide(1, H, W, blur_sigma=4.0, seed=9)[0]
+    im = np.transpose(guide, (1, 2, 0)) * np.float32(255.0)
+    assert BG.BilateralGrid(im, sigma_spatial=7, sigma_luma=8, sigma_chroma=2).range_ok
+    assert not BG.BilateralGrid(im * np.float32(40.0), sigma_spatial=7, sigma_luma=8, sigma_chroma=2).range_ok
+    assert not BG.BilateralGrid(-im, sigma_spatial=7, sigma_luma=8, sigma_chroma=2).range_ok
+    sig, bsp = BL._PRESETS[4]
+    rng = np.random.default_rng(1)
+    g4 = bo.synth_guide(1, H, W, blur_sigma=4.0, seed=10)
+    pred = rng.random((1, 1, H, W)).astype(np.float32)
+    conf = (0.05 + 0.95 * rng.random((1, 1, H, W))).astype(np.float32)
+    gout = rng.standard_normal((1, 1, H, W)).astype(np.float32)
+    o_out, yh, _ = bo.bilateral_forward(g4, pred, conf, sig, (bsp[0], bsp[1], bsp[2], 256))
+    BL.CG_LEGACY_CONVERGE = True
+    try:
+        out, gp, gc = _apply(BL, g4, pred, conf, gout, list(sig), list(bsp))
+    finally:
+        BL.CG_LEGACY_CONVERGE = False
+    assert relerr(out, o_out) <= 1e-4
