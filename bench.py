@@ -518,8 +518,10 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = peaks()
-        bwd_bytes = (20 + 14 * K) * 4 * npx      # reads 13+7K, writes 7K+7 floats per pixel
-        fwd_bytes = (13 + 7 * K) * 4 * npx       # reads 7+7K, writes 6
+        # algorithmic bytes per pixel: the forward reads 7K+7 floats and writes 6 + the 2K-float side tensor of
+        # per-lobe hemisphere sums; the backward reads 7K+13 + that side tensor and writes 7K+7
+        bwd_bytes = (20 + 14 * K + 2 * K) * 4 * npx
+        fwd_bytes = (13 + 7 * K + 2 * K) * 4 * npx
         ach = bwd_bytes / (bwd_ms * 1e-3) / 1e9
         clk = clocks.summary()
         nm = ncu_metrics()
