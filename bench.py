@@ -94,7 +94,7 @@ def synth(B, Hh, Ww, Kk, seed, device=None, pinned=False):
 # -------------------------------------------------------------------------------------------
 
 CPU_THREADS = 32          # torch CPU elementwise ops on these tensors stop scaling around 16-32 threads (profiles/r01)
-CPU_ROWS = 64             # cpu_baseline sample: 64 x 320 pixels per step
+CPU_ROWS = 240            # cpu_baseline sample: one full 240 x 320 frame per step (= BASELINE config 1; ~4 s per step)
 
 
 def cpu_threads():
@@ -163,15 +163,18 @@ def run_reference(args):
         return
     threads = cpu_threads()
     # per-step sample sized so that (steps + warmup) steps end within ~100 s, from one calibration step at CPU_ROWS
+    # per-step sample: the full frame (the same sample cpu_baseline times) whenever (steps + warmup) full-frame steps end
+    # within ~150 s, else proportionally fewer rows (calibrated with one 48-row step)
     nstep = max(1, args.steps + args.warmup)
-    step, kind = cpu_step_fn(CPU_ROWS)
+    step, kind = cpu_step_fn(48)
     step()
     t0 = time.perf_counter()
     step()
-    per_row = (time.perf_counter() - t0) / CPU_ROWS
-    rows = int(max(8, min(H, 100.0 / nstep / max(per_row, 1e-6))))
-    if rows != CPU_ROWS:
-        step, kind = cpu_step_fn(rows)
+    per_row = (time.perf_counter() - t0) / 48
+    rows = int(max(8, min(H, 150.0 / nstep / max(per_row, 1e-6))))
+    if rows > 200:
+        rows = H
+    step, kind = cpu_step_fn(rows)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
