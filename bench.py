@@ -468,26 +468,16 @@ def run_ours(args):
     out_host = torch.empty(B, 3, H, W).pin_memory()
     loss_host = torch.empty(1).pin_memory()
     copy_stream = torch.cuda.Stream(device=dev)
-    # the step's eight input tensors live back to back in ONE pinned host block and ONE device block per slot: a step's upload
-    # is a single 467 MB cudaMemcpyAsync (the tensors the API sees are views into the device block)
-    srcs_sep = list(host[:6]) + [im_host, seg_host]
-    sizes = [t.numel() for t in srcs_sep]
-    offs = [0]
-    for n_ in sizes:
-        offs.append(offs[-1] + ((n_ + 63) // 64) * 64)          # 256-byte aligned sub-tensors
-    host_block = torch.empty(offs[-1]).pin_memory()
-    for t, o, n_ in zip(srcs_sep, offs, sizes):
-        host_block[o:o + n_].copy_(t.reshape(-1))
-    dev_blocks = [torch.empty(offs[-1], device=dev) for _ in range(2)]
-    bufs = [[blk[o:o + n_].view(t.shape) for t, o, n_ in zip(srcs_sep, offs, sizes)] for blk in dev_blocks]
-    srcs = srcs_sep
+    srcs = list(host[:6]) + [im_host, seg_host]
+    bufs = [[torch.empty_like(h, device=dev) for h in srcs] for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     freed = [torch.cuda.Event(), torch.cuda.Event()]
 
     def upload(slot):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(freed[slot])          # the compute stream is done with this slot
-            dev_blocks[slot].copy_(host_block, non_blocking=True)
+            for dst, src in zip(bufs[slot], srcs):
+                dst.copy_(src, non_blocking=True)
             ready[slot].record(copy_stream)
 
     def step_e2e(slot, prefetch):
@@ -517,7 +507,7 @@ def run_ours(args):
     e1.record()
     sync_all()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1) / n_e2e, dev, world)
-    h2d = sum(h.numel() * 4 for h in srcs)      # payload bytes (the block's alignment padding is < 0.001 %)
+    h2d = sum(h.numel() * 4 for h in srcs)
     d2h = out_host.numel() * 4 + loss_host.numel() * 4
 
     # ---- the other BASELINE configs that run on this many GPUs (extras; not the headline) --------------

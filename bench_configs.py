@@ -413,6 +413,17 @@ def extras_for_bench(models, sharding, dev, rank, world, timed_ranks, make_rende
         del st
     torch.cuda.empty_cache()
     if world == 1:
+        try:
+            r = run_trainlight(models, dev, 5)
+            out['config3_wrapper_pattern'] = {
+                'what': 'the literal loss block of wrapperBRDFLight.py:177-207 on 16 images (120x160 grid): output2env (env-map MATERIALISED '
+                        'because the wrapper reads it) + LSregress + torch log-L2 + forwardEnv (fused) + LSregressDiffSpec + torch render '
+                        'loss + backward; env-free = the same losses through output2env.reconstLoss + forwardSG',
+                'ms_per_step': r['render_loss_step_ms'], 'envfree_ms_per_step': r['render_loss_step_envfree_ms'],
+                'reconst_loss_fwd_bwd_ms': r['reconst_loss_fwd_bwd_ms']}
+        except Exception as ex:
+            out['config3_wrapper_pattern'] = {'error': repr(ex)[:200]}
+        torch.cuda.empty_cache()
         out['layer_construction'] = run_ctor_cost(models)
         out['config4_bilateral'] = run_bilateral_mode0(BL, dev)
         torch.cuda.empty_cache()

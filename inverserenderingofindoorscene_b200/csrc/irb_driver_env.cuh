@@ -229,6 +229,11 @@ template <typename T> IRB_HD void drv_render_env_fwd(const RenderEnvArgs& s, con
     T A[3];
     load_pixel(px, nt, A, a, b, pix, plane);
     T Dc[3] = {0, 0, 0}, Sc[3] = {0, 0, 0};
+    // regular pixels (irb_math.cuh: unit normal, well-conditioned frame -- every real caller) shade in the local frame like
+    // the fused kernels: n.l = w_d.z is a constant and the per-direction chain is half as long as the world-space one
+    // (ncu r02: this kernel sat at 77 % issue-slot utilisation with the world-space chain)
+    PixelLocal<T> pl;
+    if (px.regular) pixel_local_setup(pl, px);
     for (int d0 = 0; d0 < D; d0 += 4) {
         const F4 e0 = ld4(s.env + ((b * 3 + 0) * plane + pix) * D + d0);
         const F4 e1 = ld4(s.env + ((b * 3 + 1) * plane + pix) * D + d0);
@@ -238,10 +243,18 @@ template <typename T> IRB_HD void drv_render_env_fwd(const RenderEnvArgs& s, con
                            {(T)e2.x, (T)e2.y, (T)e2.z, (T)e2.w}};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            Dir<T> dr;
-            dir_fwd(dr, px, (T)tab.lx[d0 + u], (T)tab.ly[d0 + u], (T)tab.lz[d0 + u]);
-            const T w = (T)tab.w[d0 + u] * dr.ndl;
-            const T ws = w * dr.spec;
+            T w, ws;
+            if (px.regular) {
+                DirL<T> dl;
+                dir_fwd_local(dl, px, pl, (T)tab.lx[d0 + u], (T)tab.ly[d0 + u], (T)tab.lz[d0 + u]);
+                w = (T)tab.w[d0 + u] * (T)tab.lz[d0 + u];
+                ws = w * dl.spec;
+            } else {
+                Dir<T> dr;
+                dir_fwd(dr, px, (T)tab.lx[d0 + u], (T)tab.ly[d0 + u], (T)tab.lz[d0 + u]);
+                w = (T)tab.w[d0 + u] * dr.ndl;
+                ws = w * dr.spec;
+            }
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 Dc[c] += w * E[c][u];
@@ -276,6 +289,12 @@ template <typename T> IRB_HD void drv_render_env_bwd(const RenderEnvArgs& s, con
     PixelGrad<T> pg;
     pixel_grad_zero(pg);
     T gAlb[3] = {0, 0, 0};
+    PixelLocal<T> pl;
+    PixelGradL<T> gl;
+    if (px.regular) {   // local-frame fast path, as in drv_render_env_fwd
+        pixel_local_setup(pl, px);
+        pixel_gradl_zero(gl);
+    }
     for (int d0 = 0; d0 < D; d0 += 4) {
         const F4 e0 = ld4(s.env + ((b * 3 + 0) * plane + pix) * D + d0);
         const F4 e1 = ld4(s.env + ((b * 3 + 1) * plane + pix) * D + d0);
@@ -287,9 +306,23 @@ template <typename T> IRB_HD void drv_render_env_bwd(const RenderEnvArgs& s, con
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const T wx = (T)tab.lx[d0 + u], wy = (T)tab.ly[d0 + u], wz = (T)tab.lz[d0 + u];
+            const T om = (T)tab.w[d0 + u];
+            if (px.regular) {
+                DirL<T> dl;
+                dir_fwd_local(dl, px, pl, wx, wy, wz);
+                const T w = om * wz;       // n.l = w_d.z: constant, no gradient through it
+                T eS = T(0);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    eS += gS[c] * E[c][u];
+                    gAlb[c] += w * E[c][u];
+                    GE[c][u] = w * (gDa[c] + gS[c] * dl.spec);
+                }
+                dir_bwd_local(gl, px, pl, dl, wx, wy, wz, w * eS);
+                continue;
+            }
             Dir<T> dr;
             dir_fwd(dr, px, wx, wy, wz);
-            const T om = (T)tab.w[d0 + u];
             const T w = om * dr.ndl;
             T eD = T(0), eS = T(0);
 #pragma unroll
@@ -308,6 +341,7 @@ template <typename T> IRB_HD void drv_render_env_bwd(const RenderEnvArgs& s, con
                     (float)GE[c][3]);
         }
     }
+    if (px.regular) gradl_to_world(pg, gl, px);
     V3<T> g_nt;
     T g_rough;
     pixel_bwd_finish(pg, px, nt, g_nt, g_rough);
