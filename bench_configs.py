@@ -170,7 +170,7 @@ def run_unfused(models, dev, iters):
     holder = {}
 
     def f1():
-        holder['env'] = o2e.output2env(a, l, w)[0]
+        holder['env'] = o2e.output2env(a, l, w)[0].materialize()   # the env-map is lazy: force the sg_to_env kernel
     res['sg_to_env_fwd_ms'] = timed(f1, iters)
     env = holder['env']
     genv = torch.rand_like(env)

@@ -19,6 +19,13 @@
 
 namespace irb {
 
+// resident 256-thread CTAs per SM the three PCG kernels are compiled for.  They are latency-bound streaming / gather kernels
+// (ncu r02: 55-85 % long-scoreboard stalls), so occupancy is memory-level parallelism: measured on one B200, config 4
+// fwd+bwd: unconstrained (44-58 registers, 4-5 CTAs) 8.06 ms, 6 CTAs (40 registers, 8-byte spills in the 3-channel
+// kernels) 6.72 ms, 8 CTAs (32 registers, real spills) 6.79 ms.
+#ifndef IRB_BG_MINB
+#define IRB_BG_MINB 6
+#endif
 constexpr int BG_DIM = 5;
 constexpr int BG_MAX_ITERS = 256;
 constexpr int BG_MAX_CH = 4;
@@ -486,7 +493,7 @@ __device__ __forceinline__ bool bg_done(void* ws, const BgLayout& L, int b, int 
 // iteration `it`, step 1:  p = z + (rho/rho_prev) p   (z = M r);  also np[v][c] = n_v p_v[c], interleaved over
 // channels so that the mat-vec's neighbour gathers fetch all channels of a vertex in ONE 32-byte sector
 template <int CH>
-__global__ void __launch_bounds__(256) bg_p_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
+__global__ void __launch_bounds__(256, IRB_BG_MINB) bg_p_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y + a.b0;
     const size_t P = L.P;
@@ -519,7 +526,7 @@ __global__ void __launch_bounds__(256) bg_p_kernel(void* ws, BgLayout L, SolveAr
 }
 
 // iteration `it`, step 2:  q = A p = lam (m p - n blur(n p)) + wsplat p ;  pq = <p,q>
-__global__ void bg_q_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
+__global__ void __launch_bounds__(256, IRB_BG_MINB) bg_q_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y + a.b0;
     const size_t P = L.P;
@@ -567,7 +574,7 @@ __global__ void bg_q_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
 
 // iteration `it`, second half: alpha = rho/pq ; x += alpha p ; r -= alpha q ; next rho, rr
 template <int CH>
-__global__ void __launch_bounds__(256) bg_xr_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
+__global__ void __launch_bounds__(256, IRB_BG_MINB) bg_xr_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y + a.b0;
     const size_t P = L.P;
