@@ -458,7 +458,7 @@ __device__ __forceinline__ double bg_matvec(F y, const double* __restrict__ n, c
 }
 
 // r0 = b - A x0 ; rho0 = <r0, M r0> ; rr0 = <r0, r0>
-__global__ void bg_r0_kernel(void* ws, BgLayout L, SolveArgs a) {
+__global__ void __launch_bounds__(256, IRB_BG_MINB) bg_r0_kernel(void* ws, BgLayout L, SolveArgs a) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y + a.b0;
     const size_t P = L.P;
@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(256, IRB_BG_MINB) bg_xr_kernel(void* ws, BgLay
 }
 
 // slice (BilateralGrid.py:93-94) -> fp32 output
-__global__ void bg_slice_kernel(const void* ws, BgLayout L, const double* __restrict__ x, float* __restrict__ out) {
+__global__ void __launch_bounds__(256, IRB_BG_MINB) bg_slice_kernel(const void* ws, BgLayout L, const double* __restrict__ x, float* __restrict__ out) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     if (t >= L.P) return;
@@ -625,7 +625,7 @@ __global__ void bg_slice_kernel(const void* ws, BgLayout L, const double* __rest
 }
 
 // backward epilogue (BilateralGrid.py:174-183, 203-205)
-__global__ void bg_grad_kernel(const void* ws, BgLayout L, const double* __restrict__ gh, const double* __restrict__ yhat,
+__global__ void __launch_bounds__(256, IRB_BG_MINB) bg_grad_kernel(const void* ws, BgLayout L, const double* __restrict__ gh, const double* __restrict__ yhat,
                                const float* __restrict__ pred, const float* __restrict__ conf, float* __restrict__ g_pred,
                                float* __restrict__ g_conf) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
