@@ -27,6 +27,16 @@
 #include "irb_tma.cuh"
 #include "irb_launch.cuh"
 
+// Resident CTAs per SM the forward / the lobe-only backward are compiled for.  Measured on one B200 (profiles/r02): forward
+// 4 / 5 / 6 -> 0.854 / 0.832 / 0.903 ms (5 = 96 registers; shared memory still caps residency at 4 CTAs, the tighter
+// register budget itself schedules better); lobe-only backward 2 / 3 / 4 -> 0.615 / 0.611 / 0.648 ms at 16 x 120 x 160.
+#ifndef IRB_FWD_MINB
+#define IRB_FWD_MINB 5
+#endif
+#ifndef IRB_LOBEONLY_MINB
+#define IRB_LOBEONLY_MINB 3
+#endif
+
 namespace irb {
 
 constexpr int kThreads = 128;
@@ -284,8 +294,8 @@ extern "C" int irb_render_sg_fwd(const float* albedo, const float* normal, const
         int rc;
         const char* w = "render_sg_fwd(group)";
 #define IRB_GROUP_FWD(TPP)                                                                                                   \
-    (K == TPP * kLPT ? launch_group(render_sg_group_kernel<0, TPP, false, false, 4, false, true>, a, tab, false, st, w, kThreads / TPP) \
-                     : launch_group(render_sg_group_kernel<0, TPP, false, false, 4>, a, tab, false, st, w, kThreads / TPP))
+    (K == TPP * kLPT ? launch_group(render_sg_group_kernel<0, TPP, false, false, IRB_FWD_MINB, false, true>, a, tab, false, st, w, kThreads / TPP) \
+                     : launch_group(render_sg_group_kernel<0, TPP, false, false, IRB_FWD_MINB>, a, tab, false, st, w, kThreads / TPP))
         if (K <= 6) rc = IRB_GROUP_FWD(1);
         else if (K <= 12) rc = IRB_GROUP_FWD(2);
         else rc = IRB_GROUP_FWD(4);
@@ -341,7 +351,7 @@ extern "C" int irb_render_sg_bwd(const float* albedo, const float* normal, const
 #define IRB_GROUP_BWD(TPP)                                                                                              \
     (pix && lobe ? (saved ? IRB_BWD_K(TPP, true, true, 2, true) : IRB_BWD_K(TPP, true, true, 2, false))                  \
      : pix       ? IRB_BWD_K(TPP, true, false, 3, false)                                                                 \
-                 : (saved ? IRB_BWD_K(TPP, false, true, 3, true) : IRB_BWD_K(TPP, false, true, 3, false)))
+                 : (saved ? IRB_BWD_K(TPP, false, true, IRB_LOBEONLY_MINB, true) : IRB_BWD_K(TPP, false, true, IRB_LOBEONLY_MINB, false)))
         if (K <= 6) rc = IRB_GROUP_BWD(1);
         else if (K <= 12) rc = IRB_GROUP_BWD(2);
         else rc = IRB_GROUP_BWD(4);

@@ -9,6 +9,10 @@
 // env-map gradient streams in as 16-byte vectors, loaded one group of 4 directions ahead of its use.
 #pragma once
 
+#ifndef IRB_SGENV_FWD_MINB
+#define IRB_SGENV_FWD_MINB 4
+#endif
+
 namespace irb {
 
 __device__ __forceinline__ void issue_sg_tile(float* stage, uint64_t* bar, const SgEnvArgs& s, const TileMaps& maps, size_t tile,
@@ -61,7 +65,7 @@ __device__ __forceinline__ float fast_log(float x) {   // natural log via lg2.ap
 }
 
 template <int MODE, int TPP>
-__global__ void __launch_bounds__(128, ((MODE == 1 || MODE >= 4) ? 3 : 4)) sg_env_group_kernel(const SgEnvArgs s, const __grid_constant__ EnvTab tab,
+__global__ void __launch_bounds__(128, ((MODE == 1 || MODE >= 4) ? 3 : IRB_SGENV_FWD_MINB)) sg_env_group_kernel(const SgEnvArgs s, const __grid_constant__ EnvTab tab,
                                                               const __grid_constant__ TileMaps maps,
                                                               const unsigned total_tiles, const unsigned tiles_per_img) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
