@@ -33,6 +33,9 @@
 #ifndef IRB_FWD_MINB
 #define IRB_FWD_MINB 5
 #endif
+#ifndef IRB_BWD_MINB
+#define IRB_BWD_MINB 2
+#endif
 #ifndef IRB_LOBEONLY_MINB
 #define IRB_LOBEONLY_MINB 3
 #endif
@@ -349,7 +352,7 @@ extern "C" int irb_render_sg_bwd(const float* albedo, const float* normal, const
     (K == TPP * kLPT ? launch_group(render_sg_group_kernel<1, TPP, PIXV, LOBEV, MINBV, SAVEDV, true>, a, tab, true, st, w, kThreads / TPP, SAVEDV) \
                      : launch_group(render_sg_group_kernel<1, TPP, PIXV, LOBEV, MINBV, SAVEDV, false>, a, tab, true, st, w, kThreads / TPP, SAVEDV))
 #define IRB_GROUP_BWD(TPP)                                                                                              \
-    (pix && lobe ? (saved ? IRB_BWD_K(TPP, true, true, 2, true) : IRB_BWD_K(TPP, true, true, 2, false))                  \
+    (pix && lobe ? (saved ? IRB_BWD_K(TPP, true, true, IRB_BWD_MINB, true) : IRB_BWD_K(TPP, true, true, IRB_BWD_MINB, false))                  \
      : pix       ? IRB_BWD_K(TPP, true, false, 3, false)                                                                 \
                  : (saved ? IRB_BWD_K(TPP, false, true, IRB_LOBEONLY_MINB, true) : IRB_BWD_K(TPP, false, true, IRB_LOBEONLY_MINB, false)))
         if (K <= 6) rc = IRB_GROUP_BWD(1);
