@@ -1,3 +1,5 @@
+# What the round-end validation on a B200 box ran (gpurun --timeout 2700 -- bash tools/gpu_round_end.sh): GPU tests, the bench
+# line, the ncu launch list and --set full captures behind profiles/r02.  tools/_run5.sh / _run7.sh: the 2- and 8-GPU lines.
 mkdir -p gpurun_out/r2m
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/r2m/pytest.log
 timeout 500 python bench.py --steps 20 --warmup 5 > gpurun_out/r2m/bench.json 2> gpurun_out/r2m/bench.err
