@@ -159,13 +159,13 @@ def run_trainlight_ddp(models, dev, iters):
             'n_gpus': world, 'step_ms_max_over_ranks': ms, 'images_per_s': world * B / ms * 1e3, 'scaling': 'weak'}
 
 
-def run_unfused(models, dev, iters):
-    B, R, C, K = 4, 240, 320, 12
+def run_unfused(models, dev, iters, B=4):
+    R, C, K = 240, 320, 12
     alb, n, rg, ax, lam, wt = rand_inputs(B, R, C, R, C, K, dev, 1237)
     rl = models.renderingLayer(imWidth=C, imHeight=R, isCuda=True)
     o2e = models.output2env(K, isCuda=True)
     npx = B * R * C
-    res = {'config': 'unfused boundary kernels, 4x240x320, 12 SG (env-map 472 MB)'}
+    res = {'config': 'unfused boundary kernels, %dx240x320, 12 SG (env-map %d MB)' % (B, B * 3 * R * C * 128 * 4 // 1000000)}
     a, l, w = [t.detach().requires_grad_(True) for t in (ax, lam, wt)]
     holder = {}
 
@@ -434,6 +434,7 @@ def extras_for_bench(models, sharding, dev, rank, world, timed_ranks, make_rende
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--which', default='trainlight,unfused,bilateral,k24,torchcuda')
+    ap.add_argument('--unfused-batch', type=int, default=4, help='images in the unfused-kernel config (4: 472 MB env-map; 16: 1.9 GB)')
     ap.add_argument('--iters', type=int, default=10)
     args = ap.parse_args()
     from inverserenderingofindoorscene_b200 import BilateralLayer as BL
@@ -462,7 +463,7 @@ def main():
         elif w == 'trainlight_ddp':
             r = run_trainlight_ddp(models, dev, args.iters)
         elif w == 'unfused':
-            r = run_unfused(models, dev, args.iters)
+            r = run_unfused(models, dev, args.iters, args.unfused_batch)
         elif w == 'bilateral':
             r = run_bilateral(BL, dev, args.iters)
         elif w == 'k24':

@@ -220,27 +220,40 @@ IRB_HD RenderSgArgs as_render_args(const RenderEnvArgs& s) {
     return a;
 }
 
-template <typename T> IRB_HD void drv_render_env_fwd(const RenderEnvArgs& s, const EnvTab& tab, size_t b, size_t pix) {
-    const RenderSgArgs a = as_render_args(s);
-    const size_t plane = (size_t)s.R * s.C;
-    const int D = tab.D;
+// Per-pixel state of render_env: begin / one call per block of 4 directions / end.  Shared by the plain thread-per-pixel
+// drivers below (global 16-byte loads) and the TMA-staged kernels of irb_render_env_tma.cuh (env tiles in shared memory).
+// Regular pixels (irb_math.cuh: unit normal, well-conditioned frame -- every real caller) shade in the local frame like the
+// fused kernels: n.l = w_d.z is a constant and the per-direction chain is half as long as the world-space one.
+template <typename T> struct RenderEnvPixel {
     Pixel<T> px;
     V3<T> nt;
     T A[3];
-    load_pixel(px, nt, A, a, b, pix, plane);
-    T Dc[3] = {0, 0, 0}, Sc[3] = {0, 0, 0};
-    // regular pixels (irb_math.cuh: unit normal, well-conditioned frame -- every real caller) shade in the local frame like
-    // the fused kernels: n.l = w_d.z is a constant and the per-direction chain is half as long as the world-space one
-    // (ncu r02: this kernel sat at 77 % issue-slot utilisation with the world-space chain)
     PixelLocal<T> pl;
-    if (px.regular) pixel_local_setup(pl, px);
-    for (int d0 = 0; d0 < D; d0 += 4) {
-        const F4 e0 = ld4(s.env + ((b * 3 + 0) * plane + pix) * D + d0);
-        const F4 e1 = ld4(s.env + ((b * 3 + 1) * plane + pix) * D + d0);
-        const F4 e2 = ld4(s.env + ((b * 3 + 2) * plane + pix) * D + d0);
-        const T E[3][4] = {{(T)e0.x, (T)e0.y, (T)e0.z, (T)e0.w},
-                           {(T)e1.x, (T)e1.y, (T)e1.z, (T)e1.w},
-                           {(T)e2.x, (T)e2.y, (T)e2.z, (T)e2.w}};
+    T Dc[3], Sc[3];                       // forward accumulators
+    T gD[3], gS[3], gDa[3], gAlb[3];      // backward
+    PixelGrad<T> pg;
+    PixelGradL<T> gl;
+
+    IRB_HD void begin(const RenderEnvArgs& s, size_t b, size_t pix, size_t plane, bool bwd) {
+        const RenderSgArgs a = as_render_args(s);
+        load_pixel(px, nt, A, a, b, pix, plane);
+        if (px.regular) pixel_local_setup(pl, px);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Dc[c] = Sc[c] = gAlb[c] = T(0);
+        if (bwd) {
+            const size_t o3 = (b * 3) * plane + pix;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                gD[c] = (T)s.g_diff[o3 + c * plane];
+                gS[c] = (T)s.g_spec[o3 + c * plane];
+                gDa[c] = gD[c] * A[c] * Consts<T>::INV_PI;
+            }
+            pixel_grad_zero(pg);
+            pixel_gradl_zero(gl);
+        }
+    }
+    // E[c][u] = env[c][d0 + u]
+    IRB_HD void quad_fwd(const EnvTab& tab, int d0, const T (&E)[3][4]) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             T w, ws;
@@ -262,47 +275,16 @@ template <typename T> IRB_HD void drv_render_env_fwd(const RenderEnvArgs& s, con
             }
         }
     }
-    const size_t o3 = (b * 3) * plane + pix;
+    IRB_HD void end_fwd(const RenderEnvArgs& s, size_t b, size_t pix, size_t plane) const {
+        const size_t o3 = (b * 3) * plane + pix;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        s.out_diff[o3 + c * plane] = (float)(A[c] * Consts<T>::INV_PI * Dc[c]);
-        s.out_spec[o3 + c * plane] = (float)Sc[c];
+        for (int c = 0; c < 3; ++c) {
+            s.out_diff[o3 + c * plane] = (float)(A[c] * Consts<T>::INV_PI * Dc[c]);
+            s.out_spec[o3 + c * plane] = (float)Sc[c];
+        }
     }
-}
-
-template <typename T> IRB_HD void drv_render_env_bwd(const RenderEnvArgs& s, const EnvTab& tab, size_t b, size_t pix) {
-    const RenderSgArgs a = as_render_args(s);
-    const size_t plane = (size_t)s.R * s.C;
-    const int D = tab.D;
-    Pixel<T> px;
-    V3<T> nt;
-    T A[3];
-    load_pixel(px, nt, A, a, b, pix, plane);
-    const size_t o3 = (b * 3) * plane + pix;
-    T gD[3], gS[3], gDa[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        gD[c] = (T)s.g_diff[o3 + c * plane];
-        gS[c] = (T)s.g_spec[o3 + c * plane];
-        gDa[c] = gD[c] * A[c] * Consts<T>::INV_PI;
-    }
-    PixelGrad<T> pg;
-    pixel_grad_zero(pg);
-    T gAlb[3] = {0, 0, 0};
-    PixelLocal<T> pl;
-    PixelGradL<T> gl;
-    if (px.regular) {   // local-frame fast path, as in drv_render_env_fwd
-        pixel_local_setup(pl, px);
-        pixel_gradl_zero(gl);
-    }
-    for (int d0 = 0; d0 < D; d0 += 4) {
-        const F4 e0 = ld4(s.env + ((b * 3 + 0) * plane + pix) * D + d0);
-        const F4 e1 = ld4(s.env + ((b * 3 + 1) * plane + pix) * D + d0);
-        const F4 e2 = ld4(s.env + ((b * 3 + 2) * plane + pix) * D + d0);
-        const T E[3][4] = {{(T)e0.x, (T)e0.y, (T)e0.z, (T)e0.w},
-                           {(T)e1.x, (T)e1.y, (T)e1.z, (T)e1.w},
-                           {(T)e2.x, (T)e2.y, (T)e2.z, (T)e2.w}};
-        T GE[3][4];
+    // GE[c][u] = dL/d env[c][d0 + u]
+    IRB_HD void quad_bwd(const EnvTab& tab, int d0, const T (&E)[3][4], T (&GE)[3][4]) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const T wx = (T)tab.lx[d0 + u], wy = (T)tab.ly[d0 + u], wz = (T)tab.lz[d0 + u];
@@ -334,6 +316,57 @@ template <typename T> IRB_HD void drv_render_env_bwd(const RenderEnvArgs& s, con
             }
             dir_bwd(pg, px, dr, wx, wy, wz, om * eD, om * eS);
         }
+    }
+    IRB_HD void end_bwd(const RenderEnvArgs& s, size_t b, size_t pix, size_t plane) {
+        const size_t o3 = (b * 3) * plane + pix;
+        if (px.regular) gradl_to_world(pg, gl, px);
+        V3<T> g_nt;
+        T g_rough;
+        pixel_bwd_finish(pg, px, nt, g_nt, g_rough);
+        if (s.g_normal) {
+            s.g_normal[o3] = (float)g_nt.x;
+            s.g_normal[o3 + plane] = (float)g_nt.y;
+            s.g_normal[o3 + 2 * plane] = (float)g_nt.z;
+        }
+        if (s.g_rough) s.g_rough[b * plane + pix] = (float)g_rough;
+        if (s.g_albedo) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) s.g_albedo[o3 + c * plane] = (float)(gD[c] * Consts<T>::INV_PI * gAlb[c]);
+        }
+    }
+};
+
+template <typename T> IRB_HD void drv_render_env_fwd(const RenderEnvArgs& s, const EnvTab& tab, size_t b, size_t pix) {
+    const size_t plane = (size_t)s.R * s.C;
+    const int D = tab.D;
+    RenderEnvPixel<T> st;
+    st.begin(s, b, pix, plane, false);
+    for (int d0 = 0; d0 < D; d0 += 4) {
+        const F4 e0 = ld4(s.env + ((b * 3 + 0) * plane + pix) * D + d0);
+        const F4 e1 = ld4(s.env + ((b * 3 + 1) * plane + pix) * D + d0);
+        const F4 e2 = ld4(s.env + ((b * 3 + 2) * plane + pix) * D + d0);
+        const T E[3][4] = {{(T)e0.x, (T)e0.y, (T)e0.z, (T)e0.w},
+                           {(T)e1.x, (T)e1.y, (T)e1.z, (T)e1.w},
+                           {(T)e2.x, (T)e2.y, (T)e2.z, (T)e2.w}};
+        st.quad_fwd(tab, d0, E);
+    }
+    st.end_fwd(s, b, pix, plane);
+}
+
+template <typename T> IRB_HD void drv_render_env_bwd(const RenderEnvArgs& s, const EnvTab& tab, size_t b, size_t pix) {
+    const size_t plane = (size_t)s.R * s.C;
+    const int D = tab.D;
+    RenderEnvPixel<T> st;
+    st.begin(s, b, pix, plane, true);
+    for (int d0 = 0; d0 < D; d0 += 4) {
+        const F4 e0 = ld4(s.env + ((b * 3 + 0) * plane + pix) * D + d0);
+        const F4 e1 = ld4(s.env + ((b * 3 + 1) * plane + pix) * D + d0);
+        const F4 e2 = ld4(s.env + ((b * 3 + 2) * plane + pix) * D + d0);
+        const T E[3][4] = {{(T)e0.x, (T)e0.y, (T)e0.z, (T)e0.w},
+                           {(T)e1.x, (T)e1.y, (T)e1.z, (T)e1.w},
+                           {(T)e2.x, (T)e2.y, (T)e2.z, (T)e2.w}};
+        T GE[3][4];
+        st.quad_bwd(tab, d0, E, GE);
         if (s.g_env) {
 #pragma unroll
             for (int c = 0; c < 3; ++c)
@@ -341,20 +374,7 @@ template <typename T> IRB_HD void drv_render_env_bwd(const RenderEnvArgs& s, con
                     (float)GE[c][3]);
         }
     }
-    if (px.regular) gradl_to_world(pg, gl, px);
-    V3<T> g_nt;
-    T g_rough;
-    pixel_bwd_finish(pg, px, nt, g_nt, g_rough);
-    if (s.g_normal) {
-        s.g_normal[o3] = (float)g_nt.x;
-        s.g_normal[o3 + plane] = (float)g_nt.y;
-        s.g_normal[o3 + 2 * plane] = (float)g_nt.z;
-    }
-    if (s.g_rough) s.g_rough[b * plane + pix] = (float)g_rough;
-    if (s.g_albedo) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) s.g_albedo[o3 + c * plane] = (float)(gD[c] * Consts<T>::INV_PI * gAlb[c]);
-    }
+    st.end_bwd(s, b, pix, plane);
 }
 
 }  // namespace irb

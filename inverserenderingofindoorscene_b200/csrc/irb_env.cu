@@ -15,6 +15,7 @@
 #include "irb_tma.cuh"
 #include "irb_launch.cuh"
 #include "irb_sg_env_group.cuh"
+#include "irb_render_env_tma.cuh"
 
 namespace irb {
 
@@ -84,6 +85,37 @@ static bool sg_group_ok(const SgEnvArgs& s, const void* extra) {
     for (const void* p : ptrs)
         if (((uintptr_t)p & 15u) != 0) return false;
     return true;
+}
+
+// TMA-staged render_env (irb_render_env_tma.cuh); returns -100 when the shape does not qualify (caller takes the plain kernel)
+template <bool BWD>
+static int launch_render_env_tma(const RenderEnvArgs& s, const EnvTab& tab, cudaStream_t st, const char* what) {
+    const char* v = getenv("IRB_RENDER_ENV_VARIANT");
+    if (v && v[0] == 'p') return -100;
+    const size_t plane = (size_t)s.R * s.C;
+    constexpr unsigned DC = ReCfg<BWD>::DC;
+    if (tab.D % DC != 0 || plane >= 0x7fffffffull) return -100;
+    EnvTileMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    if (!cached_env_tile_map(&maps.env, s.env, plane, (unsigned)tab.D, (size_t)s.B * 3, DC)) return -100;
+    if (BWD && s.g_env && !cached_env_tile_map(&maps.genv, s.g_env, plane, (unsigned)tab.D, (size_t)s.B * 3, DC)) return -100;
+    const size_t tiles_per_img = (plane + RE_PT - 1) / RE_PT;
+    const size_t total = tiles_per_img * (size_t)s.B;
+    if (total >= 0x7fffffffull) return -100;
+    const size_t smem = (size_t)RE_S * ReCfg<BWD>::STAGE_BYTES + 2 * RE_S * sizeof(uint64_t);
+    int per_sm = 1;
+    if (int e = persistent_ctas_per_sm(render_env_tma_kernel<BWD>, RE_PT, smem, &per_sm)) {
+        set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", what, smem, cudaGetErrorString((cudaError_t)e));
+        return e;
+    }
+    size_t grid = (size_t)cached_sms() * per_sm;
+    if (grid > total) grid = total;
+    if (const char* cap = getenv("IRB_TMA_MAX_CTAS")) {
+        const long c = atol(cap);
+        if (c > 0 && (size_t)c < grid) grid = (size_t)c;
+    }
+    render_env_tma_kernel<BWD><<<(unsigned)grid, RE_PT, smem, st>>>(s, tab, maps, (unsigned)total, (unsigned)tiles_per_img);
+    return check_launch(what);
 }
 
 static int mk_tab(EnvTab& tab, int envH, int envW, int B, const char* who) {
@@ -227,6 +259,10 @@ extern "C" int irb_render_env_fwd(const float* albedo, const float* normal, cons
     s.albedo = albedo; s.normal = normal; s.rough = rough; s.env = env; s.view = view;
     s.out_diff = out_diff; s.out_spec = out_spec;
     s.B = B; s.R = R; s.C = C; s.F0 = F0;
+    {
+        const int rc = launch_render_env_tma<false>(s, tab, (cudaStream_t)stream, "render_env_fwd(tma)");
+        if (rc != -100) return rc;
+    }
     const dim3 grid((unsigned)(((size_t)R * C + kThreadsEnv - 1) / kThreadsEnv), (unsigned)B);
     render_env_fwd_kernel<<<grid, kThreadsEnv, 0, (cudaStream_t)stream>>>(s, tab);
     return check_launch("render_env_fwd");
@@ -246,6 +282,10 @@ extern "C" int irb_render_env_bwd(const float* albedo, const float* normal, cons
     s.g_diff = g_diff; s.g_spec = g_spec;
     s.g_albedo = g_albedo; s.g_normal = g_normal; s.g_rough = g_rough; s.g_env = g_env;
     s.B = B; s.R = R; s.C = C; s.F0 = F0;
+    {
+        const int rc = launch_render_env_tma<true>(s, tab, (cudaStream_t)stream, "render_env_bwd(tma)");
+        if (rc != -100) return rc;
+    }
     const dim3 grid((unsigned)(((size_t)R * C + kThreadsEnv - 1) / kThreadsEnv), (unsigned)B);
     render_env_bwd_kernel<<<grid, kThreadsEnv, 0, (cudaStream_t)stream>>>(s, tab);
     return check_launch("render_env_bwd");

@@ -47,6 +47,9 @@ def test_sass_uses_the_blackwell_data_path(built):
         sass = subprocess.run(['cuobjdump', '-sass', built], capture_output=True, text=True).stdout
     for mnemonic in ('UTMALDG', 'UBLKCP', 'SYNCS', 'FFMA2', 'FMUL2', 'MUFU.EX2'):
         assert mnemonic in sass, mnemonic
+    # the TMA-staged render_env kernels send the env-map gradient tile home with tensor-map stores
+    sass_env = subprocess.run(['cuobjdump', '-sass', built], capture_output=True, text=True).stdout
+    assert 'UTMASTG' in sass_env and 'render_env_tma_kernel' in sass_env
 
 
 def test_reference_api_surface():
