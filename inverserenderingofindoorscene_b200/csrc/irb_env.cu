@@ -16,6 +16,7 @@
 #include "irb_launch.cuh"
 #include "irb_sg_env_group.cuh"
 #include "irb_render_env_tma.cuh"
+#include "irb_sg_env_tile.cuh"
 
 namespace irb {
 
@@ -118,6 +119,34 @@ static int launch_render_env_tma(const RenderEnvArgs& s, const EnvTab& tab, cuda
     return check_launch(what);
 }
 
+// thread-per-pixel, TMA-stored sg_to_env forward (irb_sg_env_tile.cuh) for K = 6 / 12; -100 = does not qualify
+template <int KC>
+static int launch_sg_env_tile_fwd(const SgEnvArgs& s, const EnvTab& tab, cudaStream_t st, const char* what) {
+    const size_t plane = (size_t)s.R * s.C;
+    constexpr unsigned DC = IRB_SGT_DC;
+    if (tab.D % DC != 0 || plane >= 0x7fffffffull) return -100;
+    CUtensorMap emap;
+    memset(&emap, 0, sizeof(emap));
+    if (!cached_env_tile_map(&emap, s.env, plane, (unsigned)tab.D, (size_t)s.B * 3, DC)) return -100;
+    const size_t tiles_per_img = (plane + RE_PT - 1) / RE_PT;
+    const size_t total = tiles_per_img * (size_t)s.B;
+    if (total >= 0x7fffffffull) return -100;
+    const size_t smem = (size_t)IRB_SGT_STAGES * 3 * RE_PT * DC * 4 + IRB_SGT_STAGES * (sizeof(uint64_t) + sizeof(unsigned));
+    int per_sm = 1;
+    if (int e = persistent_ctas_per_sm(sg_env_tile_fwd_kernel<KC>, RE_PT, smem, &per_sm)) {
+        set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", what, smem, cudaGetErrorString((cudaError_t)e));
+        return e;
+    }
+    size_t grid = (size_t)cached_sms() * per_sm;
+    if (grid > total) grid = total;
+    if (const char* cap = getenv("IRB_TMA_MAX_CTAS")) {
+        const long c = atol(cap);
+        if (c > 0 && (size_t)c < grid) grid = (size_t)c;
+    }
+    sg_env_tile_fwd_kernel<KC><<<(unsigned)grid, RE_PT, smem, st>>>(s, tab, emap, (unsigned)total, (unsigned)tiles_per_img);
+    return check_launch(what);
+}
+
 static int mk_tab(EnvTab& tab, int envH, int envW, int B, const char* who) {
     if (!make_env_tab(tab, envH, envW)) {
         set_error("%s: env table %dx%d unsupported (need envH*envW <= %d, multiple of 4)", who, envH, envW, IRB_MAX_DIRS);
@@ -144,6 +173,14 @@ extern "C" int irb_sg_to_env_fwd(const float* axis, const float* lamb, const flo
     SgEnvArgs s{};
     s.axis = axis; s.lamb = lamb; s.weight = weight; s.env = env; s.lamb_w = lamb_w; s.weight_w = weight_w;
     s.B = B; s.K = K; s.R = R; s.C = C; s.warp = warp;
+    {
+        const char* v = getenv("IRB_SGENV_VARIANT");
+        if (!(v && (v[0] == 'p' || v[0] == 'g')) && (K == 6 || K == 12)) {
+            const int rc = K == 12 ? launch_sg_env_tile_fwd<12>(s, tab, (cudaStream_t)stream, "sg_to_env_fwd(tile)")
+                                   : launch_sg_env_tile_fwd<6>(s, tab, (cudaStream_t)stream, "sg_to_env_fwd(tile)");
+            if (rc != -100) return rc;
+        }
+    }
     if (sg_group_ok(s, env)) {
         cudaStream_t st = (cudaStream_t)stream;
         const char* w = "sg_to_env_fwd(group)";

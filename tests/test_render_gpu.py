@@ -602,3 +602,41 @@ def test_render_env_tma_ring(irb, cap, monkeypatch):
         refs.append([dd.detach().numpy(), ss.detach().numpy()] + [x.numpy() for x in gg])
     for t, r64, r32, n in zip(tma, refs[0], refs[1], names):
         check_parity(t.cpu().numpy(), r64, r32, n)
+
+
+@pytest.mark.parametrize('K', [12, 6])
+@pytest.mark.parametrize('cap', ['1', '3'])
+def test_sg_to_env_tile_ring(irb, K, cap, monkeypatch):
+    """thread-per-pixel sg_to_env forward (env tile assembled in shared memory, 2-stage ring, tensor-map stores) with the grid
+    capped so that every CTA walks many tiles and chunks, last tile partial: against the lobe-split kernel and the fp64 oracle,
+    raw heads (output2env: tan warps inside the kernel) and physical lobes (fromSGtoIm)"""
+    from oracle import render_oracle as ro
+    B, R, C = 2, 19, 37          # plane = 703 = 5 full tiles + 63 px
+    ins64 = ro.synth_inputs(B, R, C, R, C, K, seed=77 + K, dtype=torch.float64, hi=0.9)
+    dev = torch.device('cuda')
+    o2e = irb.output2env(K, isCuda=True)
+    heads = [t.float().to(dev) for t in ins64[3:]]
+
+    def run():
+        env_w = o2e.output2env(*heads)[0].materialize().detach().clone()
+        env_p = o2e.fromSGtoIm(heads[0], heads[1].abs() * 20 + 0.1, heads[2].abs()).materialize().detach().clone()
+        torch.cuda.synchronize()
+        return env_w, env_p
+    monkeypatch.setenv('IRB_SGENV_VARIANT', 'group')
+    ref = run()
+    monkeypatch.delenv('IRB_SGENV_VARIANT')
+    monkeypatch.setenv('IRB_TMA_MAX_CTAS', cap)
+    from inverserenderingofindoorscene_b200 import _lib
+    n0 = _lib.lib().irb_launch_count()
+    tile = run()
+    assert _lib.lib().irb_launch_count() - n0 == 2
+    monkeypatch.delenv('IRB_TMA_MAX_CTAS')
+    for a, b in zip(ref, tile):
+        assert relerr(b.cpu().numpy(), a.cpu().numpy()) <= 2e-6
+    for dt, store in ((torch.float64, []), (torch.float32, [])):
+        e = ro.output2env(*[t.to(dt) for t in ins64[3:]])[0]
+        store.append(e.numpy())
+        if dt == torch.float64:
+            e64 = store[0]
+        else:
+            check_parity(tile[0].cpu().numpy(), e64, store[0], 'env')
