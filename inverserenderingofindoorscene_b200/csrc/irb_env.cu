@@ -103,7 +103,7 @@ static int launch_render_env_tma(const RenderEnvArgs& s, const EnvTab& tab, cuda
     const size_t tiles_per_img = (plane + RE_PT - 1) / RE_PT;
     const size_t total = tiles_per_img * (size_t)s.B;
     if (total >= 0x7fffffffull) return -100;
-    const size_t smem = (size_t)RE_S * ReCfg<BWD>::STAGE_BYTES + 2 * RE_S * sizeof(uint64_t);
+    const size_t smem = (size_t)RE_S * ReCfg<BWD>::STAGE_BYTES + RE_S * (sizeof(uint64_t) + sizeof(unsigned));
     int per_sm = 1;
     if (int e = persistent_ctas_per_sm(render_env_tma_kernel<BWD>, RE_PT, smem, &per_sm)) {
         set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", what, smem, cudaGetErrorString((cudaError_t)e));

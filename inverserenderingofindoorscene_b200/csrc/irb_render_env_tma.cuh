@@ -204,13 +204,13 @@ __global__ void __launch_bounds__(RE_PT, ReCfg<BWD>::MINB)
     // come first so that their swizzle atoms are aligned, the barriers follow.  Checked, not assumed.
     extern __shared__ __align__(1024) unsigned char re_smem[];
     uint64_t* const full_bar = reinterpret_cast<uint64_t*>(re_smem + RE_S * RE_STAGE_BYTES);
-    uint64_t* const empty_bar = full_bar + RE_S;
+    unsigned* const done_cnt = reinterpret_cast<unsigned*>(full_bar + RE_S);   // warps that are through with the stage
     if (threadIdx.x == 0) {
         if (smem_u32(re_smem) & 1023u) __trap();
 #pragma unroll
         for (int i = 0; i < RE_S; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], RE_PT);
+            done_cnt[i] = 0u;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(RE_PT, ReCfg<BWD>::MINB)
         tma_store_commit();
     };
     if (threadIdx.x == 0)
-        for (unsigned g = 0; g < (unsigned)(RE_S - 1) && g < G; ++g) issue(g);
+        for (unsigned g = 0; g < (unsigned)RE_S && g < G; ++g) issue(g);
 
     constexpr bool PK = BWD ? (IRB_RE_PK_BWD != 0) : (IRB_RE_PK_FWD != 0);
     RenderEnvPixelPk px;
@@ -257,23 +257,6 @@ __global__ void __launch_bounds__(RE_PT, ReCfg<BWD>::MINB)
     }
     for (unsigned g = 0; g < G; ++g) {
         const int stage = (int)(g % RE_S);
-        if (threadIdx.x == 0) {
-            // the stage chunk g + RE_S - 1 goes into was last used by chunk g - 1: wait until all 128 threads released it,
-            // send its gradient tile home (backward), then refill
-            if (g >= 1) {
-                const unsigned gp = g - 1;
-                mbar_wait(&empty_bar[gp % RE_S], (gp / RE_S) & 1);
-                if (store) {
-                    flush(gp);
-                    tma_store_wait_read();   // the bulk store has finished READING the stage
-                }
-            }
-            const unsigned r = g + RE_S - 1;
-            if (r < G) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue(r);
-            }
-        }
         const bool active = (size_t)pix0 + row < plane;
         const size_t pix = active ? (size_t)pix0 + row : (size_t)pix0;   // idle lanes shade the tile's first pixel, nothing stored
         if (d0 == 0) px.begin_pk(s, (size_t)b, pix, plane, BWD);
@@ -312,8 +295,27 @@ __global__ void __launch_bounds__(RE_PT, ReCfg<BWD>::MINB)
                 px.quad_fwd(tab, d0 + 4 * j, E);
             }
         }
+        // The warp that is through with the stage LAST sends its gradient tile home (backward) and refills it with chunk
+        // g + RE_S: no designated producer thread, so no warp waits for a particular other warp (with thread 0 as the
+        // producer warp 0 trailed every chunk and the others queued behind its refills).
         if (store) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the bulk store
-        mbar_arrive(&empty_bar[stage]);
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) {
+            unsigned old;
+            asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(&done_cnt[stage])) : "memory");
+            if (old == (unsigned)(RE_PT / 32 - 1)) {
+                done_cnt[stage] = 0u;   // untouched until the refill below has landed
+                if (store) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    flush(g);
+                    if (g + RE_S < G) tma_store_wait_read();   // the bulk store has finished READING the stage
+                }
+                if (g + RE_S < G) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(g + RE_S);
+                }
+            }
+        }
         if (d0 + RE_DC >= D && active) {
             if constexpr (!PK) {
                 if (BWD) px.end_bwd(s, (size_t)b, pix, plane);
@@ -332,14 +334,7 @@ __global__ void __launch_bounds__(RE_PT, ReCfg<BWD>::MINB)
             pix0 = (int)(tile % tiles_per_img) * RE_PT;
         }
     }
-    if (threadIdx.x == 0 && store && G > 0) {   // the last chunk's gradient tile
-        const unsigned gp = G - 1;
-        mbar_wait(&empty_bar[gp % RE_S], (gp / RE_S) & 1);
-        flush(gp);
-        tma_store_wait_all();
-    } else if (threadIdx.x == 0 && store) {
-        tma_store_wait_all();
-    }
+    if (store) tma_store_wait_all();   // threads that never stored return at once
 }
 
 }  // namespace irb

@@ -23,11 +23,11 @@ import sys
 FAMILIES = [  # (key, regex on the demangled kernel name)
     ('render_sg_fwd', r'render_sg_group_kernel<0,'),
     ('render_sg_bwd', r'render_sg_group_kernel<1,'),
-    ('sg_env_fwd', r'sg_env_group_kernel<0,'),
+    ('sg_env_fwd', r'sg_env_group_kernel<0,|sg_env_tile_fwd_kernel'),
     ('sg_env_bwd', r'sg_env_group_kernel<1,'),
     ('sg_reconst', r'sg_env_group_kernel<[2-5],'),
-    ('render_env_fwd', r'render_env_fwd'),
-    ('render_env_bwd', r'render_env_bwd'),
+    ('render_env_fwd', r'render_env_fwd|render_env_tma_kernel<0'),
+    ('render_env_bwd', r'render_env_bwd|render_env_tma_kernel<1'),
     ('bg_q', r'bg_q_kernel'), ('bg_p', r'bg_p_kernel'), ('bg_xr', r'bg_xr_kernel'), ('bg_pcg', r'bg_pcg'),
     ('render_loss', r'render_loss_kernel'), ('lsreg_stats1', r'lsreg_stats1'), ('lsreg_stats2', r'lsreg_stats2'),
 ]
