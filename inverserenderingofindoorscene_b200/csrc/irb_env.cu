@@ -88,11 +88,19 @@ static bool sg_group_ok(const SgEnvArgs& s, const void* extra) {
     return true;
 }
 
+// IRB_DISABLE_TMA=1 / IRB_TMA_TENSOR=0: the tensor-map kernels of this file step aside too
+static bool env_tiles_disabled() {
+    const char* dis = getenv("IRB_DISABLE_TMA");
+    const char* tt = getenv("IRB_TMA_TENSOR");
+    return (dis && dis[0] == '1') || (tt && tt[0] == '0');
+}
+
 // TMA-staged render_env (irb_render_env_tma.cuh); returns -100 when the shape does not qualify (caller takes the plain kernel)
 template <bool BWD>
 static int launch_render_env_tma(const RenderEnvArgs& s, const EnvTab& tab, cudaStream_t st, const char* what) {
     const char* v = getenv("IRB_RENDER_ENV_VARIANT");
     if (v && v[0] == 'p') return -100;
+    if (env_tiles_disabled()) return -100;
     const size_t plane = (size_t)s.R * s.C;
     constexpr unsigned DC = ReCfg<BWD>::DC;
     if (tab.D % DC != 0 || plane >= 0x7fffffffull) return -100;
@@ -124,7 +132,7 @@ template <int KC>
 static int launch_sg_env_tile_fwd(const SgEnvArgs& s, const EnvTab& tab, cudaStream_t st, const char* what) {
     const size_t plane = (size_t)s.R * s.C;
     constexpr unsigned DC = IRB_SGT_DC;
-    if (tab.D % DC != 0 || plane >= 0x7fffffffull) return -100;
+    if (tab.D % DC != 0 || plane >= 0x7fffffffull || env_tiles_disabled()) return -100;
     CUtensorMap emap;
     memset(&emap, 0, sizeof(emap));
     if (!cached_env_tile_map(&emap, s.env, plane, (unsigned)tab.D, (size_t)s.B * 3, DC)) return -100;

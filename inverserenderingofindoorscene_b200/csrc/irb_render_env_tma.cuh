@@ -2,16 +2,18 @@
 // env-map, models.py:466-520).  Device only.
 //
 // Why: the thread-per-pixel kernels read a pixel's 128 directions as 16-byte vectors at a 512-byte stride between lanes --
-// every warp load touches 32 different 128-byte lines and half of each 32-byte sector; ncu r02: forward 53 % of HBM peak,
-// backward 43 % with 62 % long-scoreboard stalls and 1.29x the algorithmic DRAM traffic.  Here the env-map (and in the
-// backward its gradient) moves through shared memory in tiles of 128 pixels x 16 directions x 3 channels:
-//   * tensor map over env viewed as [B*3, P, D] fp32, box {16 directions, 128 pixels, 1}, SWIZZLE_64B -- every 64-byte
-//     row of the box is one full run of a pixel's directions, the hardware XOR-swizzle makes the per-lane 16-byte reads
-//     (lane = pixel) bank-conflict free;
-//   * a 3-stage ring (24 KB per stage) with full / empty mbarriers, filled by one elected thread two chunks ahead;
+// every warp load touches 32 different 128-byte lines and half of each 32-byte sector; ncu r02: backward 62 % long-scoreboard
+// stalls and 1.29x the algorithmic DRAM traffic.  Here the env-map (and in the backward its gradient) moves through shared
+// memory in tiles of 128 pixels x DC directions x 3 channels (DC = 8 shipped, 16 kept as an A/B variant):
+//   * tensor map over env viewed as [B*3, P, D] fp32, box {DC directions, 128 pixels, 1}, swizzle span = the row (32 / 64
+//     bytes) -- every row of the box is one full run of a pixel's directions, the hardware XOR-swizzle makes the per-lane
+//     16-byte reads (lane = pixel) bank-conflict free;
+//   * a 3-stage ring with full mbarriers; the warp that is through with a stage last refills it (no producer thread);
 //   * backward: the thread that read E[c][d0..d0+3] writes dL/dE into the same slots, and the stage goes back to HBM as
-//     ONE tensor-map store per channel (cp.async.bulk.tensor ... shared -> global, SASS UTMASTG) before it is refilled.
+//     ONE tensor-map store per channel (cp.async.bulk.tensor ... shared -> global, SASS UTMASTG) before it is refilled;
+//   * regular pixels: packed f32x2 local-frame BRDF, two directions per instruction (RenderEnvPixelPk below).
 // Per-pixel math: RenderEnvPixel of irb_driver_env.cuh (the same code the plain kernels and the host check run).
+// Measurements of every step: profiles/r02/ab_render_env.txt.
 #pragma once
 
 namespace irb {
