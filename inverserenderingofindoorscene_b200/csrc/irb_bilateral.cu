@@ -483,6 +483,27 @@ __global__ void __launch_bounds__(256, IRB_BG_MINB) bg_r0_kernel(void* ws, BgLay
     }
 }
 
+// Cache policy of the PCG kernels: everything but `np` is streamed once per launch (52 doubles per vertex and iteration,
+// 5x the L2), `np` (32 B per vertex, 50 MB at config 4) is gathered ten times per vertex by bg_q.  Streaming accesses use
+// the evict-first policy (ld/st.global.cs) so that they do not push `np` out between bg_p (writes it) and bg_q.
+#ifndef IRB_BG_STREAM_HINTS
+#define IRB_BG_STREAM_HINTS 1
+#endif
+template <typename T> __device__ __forceinline__ T ld_stream(const T* p) {
+#if IRB_BG_STREAM_HINTS
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+template <typename T> __device__ __forceinline__ void st_stream(T* p, T v) {
+#if IRB_BG_STREAM_HINTS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
 __device__ __forceinline__ bool bg_done(void* ws, const BgLayout& L, int b, int c, int it, double tol) {
     const double* s = scal_ptr(ws, L, b, c, it);
     const double bb = scal_ptr(ws, L, b, c, BG_MAX_ITERS + 1)[0];
@@ -507,18 +528,18 @@ __global__ void __launch_bounds__(256, IRB_BG_MINB) bg_p_kernel(void* ws, BgLayo
         done[c] = bg_done(ws, L, b, c, it, a.tol);
         beta[c] = (it > 0 && !done[c]) ? scal_ptr(ws, L, b, c, it)[0] / scal_ptr(ws, L, b, c, it - 1)[0] : 0.0;
         const size_t o = ((size_t)b * CH + c) * P + t;
-        rv[c] = done[c] ? 0.0 : at<double>(ws, L.r)[o];
-        pold[c] = (it > 0 && !done[c]) ? pprev[o] : 0.0;
+        rv[c] = done[c] ? 0.0 : ld_stream(at<double>(ws, L.r) + o);
+        pold[c] = (it > 0 && !done[c]) ? ld_stream(pprev + o) : 0.0;
     }
-    const double nv = at<double>(ws, L.n0)[(size_t)b * P + t];
-    const double mi = at<double>(ws, L.minv)[(size_t)b * P + t];
+    const double nv = ld_stream(at<double>(ws, L.n0) + (size_t)b * P + t);
+    const double mi = ld_stream(at<double>(ws, L.minv) + (size_t)b * P + t);
     double out[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
         if (done[c]) continue;
         const double z = mi * rv[c];
         const double pv = (it > 0) ? fma(beta[c], pold[c], z) : z;
-        pnext[((size_t)b * CH + c) * P + t] = pv;
+        st_stream(pnext + ((size_t)b * CH + c) * P + t, pv);
         out[c] = nv * pv;
     }
     double4* np = at<double4>(ws, L.np) + (size_t)b * P + t;
@@ -541,7 +562,7 @@ __global__ void __launch_bounds__(256, IRB_BG_MINB) bg_q_kernel(void* ws, BgLayo
         bl[0] = 2.0 * BG_DIM * own.x; bl[1] = 2.0 * BG_DIM * own.y; bl[2] = 2.0 * BG_DIM * own.z; bl[3] = 2.0 * BG_DIM * own.w;
 #pragma unroll
         for (int d = 0; d < BG_DIM; ++d) {   // same summation order as bg_blur: per dimension (lo + hi), then accumulate
-            const int lo = nbr[(size_t)(2 * d) * P + t], hi = nbr[(size_t)(2 * d + 1) * P + t];
+            const int lo = ld_stream(nbr + (size_t)(2 * d) * P + t), hi = ld_stream(nbr + (size_t)(2 * d + 1) * P + t);
             double4 tt = make_double4(0.0, 0.0, 0.0, 0.0);
             bool any = false;
             if (lo >= 0) { tt = np[lo]; any = true; }
@@ -552,9 +573,9 @@ __global__ void __launch_bounds__(256, IRB_BG_MINB) bg_q_kernel(void* ws, BgLayo
             }
             if (any) { bl[0] += tt.x; bl[1] += tt.y; bl[2] += tt.z; bl[3] += tt.w; }
         }
-        nv = at<double>(ws, L.n0)[(size_t)b * P + t];
-        mv = at<double>(ws, L.m)[(size_t)b * P + t];
-        wsp = at<double>(ws, L.wsplat)[(size_t)b * P + t];
+        nv = ld_stream(at<double>(ws, L.n0) + (size_t)b * P + t);
+        mv = ld_stream(at<double>(ws, L.m) + (size_t)b * P + t);
+        wsp = ld_stream(at<double>(ws, L.wsplat) + (size_t)b * P + t);
     }
     double pq[BG_MAX_CH] = {0.0, 0.0, 0.0, 0.0};
     double* dst[BG_MAX_CH] = {nullptr, nullptr, nullptr, nullptr};
@@ -563,9 +584,9 @@ __global__ void __launch_bounds__(256, IRB_BG_MINB) bg_q_kernel(void* ws, BgLayo
         dst[c] = scal_ptr(ws, L, b, c, it) + 1;
         if (ok) {
             const size_t o = ((size_t)b * L.ch + c) * P + t;
-            const double pv = at<double>(ws, (it & 1) ? L.p0 : L.p1)[o];
+            const double pv = ld_stream(at<double>(ws, (it & 1) ? L.p0 : L.p1) + o);
             const double q = a.lam * (mv * pv - nv * bl[c]) + wsp * pv;
-            at<double>(ws, L.q)[o] = q;
+            st_stream(at<double>(ws, L.q) + o, q);
             pq[c] = pv * q;
         }
     }
@@ -594,20 +615,20 @@ __global__ void __launch_bounds__(256, IRB_BG_MINB) bg_xr_kernel(void* ws, BgLay
         alpha[c] = done ? 0.0 : s[0] / s[1];
         const size_t o = ((size_t)b * CH + c) * P + t;
         const bool ld = ok && !done;
-        pv[c] = ld ? pcur[o] : 0.0;
-        xv[c] = ld ? a.x[o] : 0.0;
-        rv[c] = ld ? at<double>(ws, L.r)[o] : 0.0;
-        qv[c] = ld ? at<double>(ws, L.q)[o] : 0.0;
+        pv[c] = ld ? ld_stream(pcur + o) : 0.0;
+        xv[c] = ld ? ld_stream(a.x + o) : 0.0;
+        rv[c] = ld ? ld_stream(at<double>(ws, L.r) + o) : 0.0;
+        qv[c] = ld ? ld_stream(at<double>(ws, L.q) + o) : 0.0;
     }
-    const double mi = ok ? at<double>(ws, L.minv)[(size_t)b * P + t] : 0.0;
+    const double mi = ok ? ld_stream(at<double>(ws, L.minv) + (size_t)b * P + t) : 0.0;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
         sums[2 * c] = sums[2 * c + 1] = 0.0;
         if (ok && dst[2 * c]) {
             const size_t o = ((size_t)b * CH + c) * P + t;
-            a.x[o] = xv[c] + alpha[c] * pv[c];
+            st_stream(a.x + o, xv[c] + alpha[c] * pv[c]);
             const double r = rv[c] - alpha[c] * qv[c];
-            at<double>(ws, L.r)[o] = r;
+            st_stream(at<double>(ws, L.r) + o, r);
             sums[2 * c] = r * mi * r;
             sums[2 * c + 1] = r * r;
         }

@@ -331,9 +331,10 @@ def test_lobe_counts_group_kernels(irb, K):
         check_parity(t.detach().cpu().numpy(), r64, r32, name)
 
 
-@pytest.mark.parametrize('envH,envW', [(4, 8), (8, 8), (2, 16)])
+@pytest.mark.parametrize('envH,envW', [(4, 8), (8, 8), (2, 16), (3, 8), (2, 6)])
 def test_other_env_tables(irb, envH, envW):
-    """hemisphere tables other than 8x16 (models.py ctor kwargs envWidth / envHeight), fused and unfused"""
+    """hemisphere tables other than 8x16 (models.py ctor kwargs envWidth / envHeight), fused and unfused; 24 directions: the
+    TMA-staged render_env kernels with 3 chunks, sg_to_env through the lobe-split kernel; 12 directions: the plain kernels"""
     from oracle import render_oracle as ro
     B, R, C, K = 1, 6, 8, 12
     ins64 = ro.synth_inputs(B, R, C, R, C, K, seed=77, dtype=torch.float64, hi=0.9)
