@@ -636,6 +636,156 @@ __global__ void __launch_bounds__(256, IRB_BG_MINB) bg_xr_kernel(void* ws, BgLay
     block_atomic_add_n<2 * CH>(sums, dst);
 }
 
+// ---- record form of the three PCG kernels (1..3 channels) -------------------------------------------------------------
+// The legacy kernels above keep the search direction twice: p (channel-major, ping-pong) and np = n * p (vertex-major, what
+// the neighbour gathers read).  Here ONE vertex-major record {p_0..p_{CH-1}, n} (double2 for one channel, double4 for 2-3)
+// replaces both: bg_q multiplies n_j * p_j after the gather -- the same rounded product that bg_p used to store (__dmul_rn, not
+// contracted), so the arithmetic of the solve is unchanged (results still vary in the last bits with the order of the fp64
+// atomics of the dot products, as before) -- and the own p and n come out of the same load.  Doubles moved per vertex
+// and iteration: 3 channels 52 -> 46, 1 channel 30 -> 24; a one-channel gather fetches 16 instead of 32 bytes.
+#ifndef IRB_BG_RECORDS
+#define IRB_BG_RECORDS 1
+#endif
+template <int CH> struct BgRec { typedef double4 T; };
+template <> struct BgRec<1> { typedef double2 T; };
+template <int CH> __device__ __forceinline__ void rec_unpack(const typename BgRec<CH>::T& r, double (&p)[3], double& n);
+template <> __device__ __forceinline__ void rec_unpack<1>(const double2& r, double (&p)[3], double& n) { p[0] = r.x; p[1] = p[2] = 0.0; n = r.y; }
+template <> __device__ __forceinline__ void rec_unpack<2>(const double4& r, double (&p)[3], double& n) { p[0] = r.x; p[1] = r.y; p[2] = 0.0; n = r.w; }
+template <> __device__ __forceinline__ void rec_unpack<3>(const double4& r, double (&p)[3], double& n) { p[0] = r.x; p[1] = r.y; p[2] = r.z; n = r.w; }
+template <int CH> __device__ __forceinline__ typename BgRec<CH>::T rec_pack(const double (&p)[3], double n);
+template <> __device__ __forceinline__ double2 rec_pack<1>(const double (&p)[3], double n) { return make_double2(p[0], n); }
+template <> __device__ __forceinline__ double4 rec_pack<2>(const double (&p)[3], double n) { return make_double4(p[0], p[1], 0.0, n); }
+template <> __device__ __forceinline__ double4 rec_pack<3>(const double (&p)[3], double n) { return make_double4(p[0], p[1], p[2], n); }
+
+template <int CH>
+__global__ void __launch_bounds__(256, IRB_BG_MINB) bg_p_rec_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
+    typedef typename BgRec<CH>::T Rec;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y + a.b0;
+    const size_t P = L.P;
+    if (t >= (size_t)at<int>(ws, L.hdr)[b]) return;
+    Rec* rec = at<Rec>(ws, L.np) + (size_t)b * P + t;
+    bool done[CH];
+    double beta[CH], rv[CH], pold[3] = {0.0, 0.0, 0.0}, nv;
+    if (it > 0) rec_unpack<CH>(*rec, pold, nv);
+    else nv = ld_stream(at<double>(ws, L.n0) + (size_t)b * P + t);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        done[c] = bg_done(ws, L, b, c, it, a.tol);
+        beta[c] = (it > 0 && !done[c]) ? scal_ptr(ws, L, b, c, it)[0] / scal_ptr(ws, L, b, c, it - 1)[0] : 0.0;
+        rv[c] = done[c] ? 0.0 : ld_stream(at<double>(ws, L.r) + ((size_t)b * CH + c) * P + t);
+    }
+    const double mi = ld_stream(at<double>(ws, L.minv) + (size_t)b * P + t);
+    double pn[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        if (done[c]) continue;   // a finished channel's slot reads as 0, nobody uses it
+        const double z = mi * rv[c];
+        pn[c] = (it > 0) ? fma(beta[c], pold[c], z) : z;
+    }
+    *rec = rec_pack<CH>(pn, nv);
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256, IRB_BG_MINB) bg_q_rec_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
+    typedef typename BgRec<CH>::T Rec;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y + a.b0;
+    const size_t P = L.P;
+    const int V = at<int>(ws, L.hdr)[b];
+    const bool ok = t < (size_t)V;
+    double bl[3] = {0.0, 0.0, 0.0}, pv[3] = {0.0, 0.0, 0.0};
+    double nv = 0.0, mv = 0.0, wsp = 0.0;
+    if (ok) {
+        const Rec* rec = at<Rec>(ws, L.np) + (size_t)b * P;
+        const int* nbr = at<int>(ws, L.nbr) + (size_t)b * 2 * BG_DIM * P;
+        rec_unpack<CH>(rec[t], pv, nv);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) bl[c] = 2.0 * BG_DIM * __dmul_rn(nv, pv[c]);
+#pragma unroll
+        for (int d = 0; d < BG_DIM; ++d) {   // same summation order as bg_blur: per dimension (lo + hi), then accumulate
+            const int lo = ld_stream(nbr + (size_t)(2 * d) * P + t), hi = ld_stream(nbr + (size_t)(2 * d + 1) * P + t);
+            double tt[3] = {0.0, 0.0, 0.0};
+            bool any = false;
+            if (lo >= 0) {
+                double pj[3], nj;
+                rec_unpack<CH>(rec[lo], pj, nj);
+#pragma unroll
+                for (int c = 0; c < CH; ++c) tt[c] = __dmul_rn(nj, pj[c]);   // rounded product, never contracted into the add below
+                any = true;
+            }
+            if (hi >= 0) {
+                double pj[3], nj;
+                rec_unpack<CH>(rec[hi], pj, nj);
+#pragma unroll
+                for (int c = 0; c < CH; ++c) tt[c] = any ? tt[c] + __dmul_rn(nj, pj[c]) : __dmul_rn(nj, pj[c]);
+                any = true;
+            }
+            if (any) {
+#pragma unroll
+                for (int c = 0; c < CH; ++c) bl[c] += tt[c];
+            }
+        }
+        mv = ld_stream(at<double>(ws, L.m) + (size_t)b * P + t);
+        wsp = ld_stream(at<double>(ws, L.wsplat) + (size_t)b * P + t);
+    }
+    double pq[BG_MAX_CH] = {0.0, 0.0, 0.0, 0.0};
+    double* dst[BG_MAX_CH] = {nullptr, nullptr, nullptr, nullptr};
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        if (bg_done(ws, L, b, c, it, a.tol)) continue;  // uniform per (image, channel)
+        dst[c] = scal_ptr(ws, L, b, c, it) + 1;
+        if (ok) {
+            const double q = a.lam * (mv * pv[c] - nv * bl[c]) + wsp * pv[c];
+            st_stream(at<double>(ws, L.q) + ((size_t)b * CH + c) * P + t, q);
+            pq[c] = pv[c] * q;
+        }
+    }
+    block_atomic_add_n<BG_MAX_CH>(pq, dst);
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256, IRB_BG_MINB) bg_xr_rec_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
+    typedef typename BgRec<CH>::T Rec;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y + a.b0;
+    const size_t P = L.P;
+    const int V = at<int>(ws, L.hdr)[b];
+    const bool ok = t < (size_t)V;
+    double sums[2 * CH];
+    double* dst[2 * CH];
+    double alpha[CH], pv[3] = {0.0, 0.0, 0.0}, xv[CH], rv[CH], qv[CH], nv;
+    if (ok) rec_unpack<CH>(at<Rec>(ws, L.np)[(size_t)b * P + t], pv, nv);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {   // all loads first, then the arithmetic, then one reduction for the 2*CH sums
+        const bool done = bg_done(ws, L, b, c, it, a.tol);
+        const double* s = scal_ptr(ws, L, b, c, it);
+        double* sn = scal_ptr(ws, L, b, c, it + 1);
+        dst[2 * c] = done ? nullptr : sn + 0;
+        dst[2 * c + 1] = done ? nullptr : sn + 2;
+        alpha[c] = done ? 0.0 : s[0] / s[1];
+        const size_t o = ((size_t)b * CH + c) * P + t;
+        const bool ld = ok && !done;
+        xv[c] = ld ? ld_stream(a.x + o) : 0.0;
+        rv[c] = ld ? ld_stream(at<double>(ws, L.r) + o) : 0.0;
+        qv[c] = ld ? ld_stream(at<double>(ws, L.q) + o) : 0.0;
+    }
+    const double mi = ok ? ld_stream(at<double>(ws, L.minv) + (size_t)b * P + t) : 0.0;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        sums[2 * c] = sums[2 * c + 1] = 0.0;
+        if (ok && dst[2 * c]) {
+            const size_t o = ((size_t)b * CH + c) * P + t;
+            st_stream(a.x + o, xv[c] + alpha[c] * pv[c]);
+            const double r = rv[c] - alpha[c] * qv[c];
+            st_stream(at<double>(ws, L.r) + o, r);
+            sums[2 * c] = r * mi * r;
+            sums[2 * c + 1] = r * r;
+        }
+    }
+    block_atomic_add_n<2 * CH>(sums, dst);
+}
+
 // slice (BilateralGrid.py:93-94) -> fp32 output
 __global__ void __launch_bounds__(256, IRB_BG_MINB) bg_slice_kernel(const void* ws, BgLayout L, const double* __restrict__ x, float* __restrict__ out) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -686,6 +836,28 @@ static int run_pcg(void* ws, const BgLayout& L, SolveArgs a, int maxiter, cudaSt
         bg_setup_kernel<<<grid, 256, 0, st>>>(ws, L, a);
         bg_r0_kernel<<<grid, 256, 0, st>>>(ws, L, a);
         for (int it = 0; it < maxiter; ++it) {
+#if IRB_BG_RECORDS
+            if (L.ch <= 3) {
+                switch (L.ch) {
+                    case 1:
+                        bg_p_rec_kernel<1><<<grid, 256, 0, st>>>(ws, L, a, it);
+                        bg_q_rec_kernel<1><<<grid, 256, 0, st>>>(ws, L, a, it);
+                        bg_xr_rec_kernel<1><<<grid, 256, 0, st>>>(ws, L, a, it);
+                        break;
+                    case 2:
+                        bg_p_rec_kernel<2><<<grid, 256, 0, st>>>(ws, L, a, it);
+                        bg_q_rec_kernel<2><<<grid, 256, 0, st>>>(ws, L, a, it);
+                        bg_xr_rec_kernel<2><<<grid, 256, 0, st>>>(ws, L, a, it);
+                        break;
+                    default:
+                        bg_p_rec_kernel<3><<<grid, 256, 0, st>>>(ws, L, a, it);
+                        bg_q_rec_kernel<3><<<grid, 256, 0, st>>>(ws, L, a, it);
+                        bg_xr_rec_kernel<3><<<grid, 256, 0, st>>>(ws, L, a, it);
+                        break;
+                }
+                continue;
+            }
+#endif
             switch (L.ch) {
                 case 1: bg_p_kernel<1><<<grid, 256, 0, st>>>(ws, L, a, it); break;
                 case 2: bg_p_kernel<2><<<grid, 256, 0, st>>>(ws, L, a, it); break;
