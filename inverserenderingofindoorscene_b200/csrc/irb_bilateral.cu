@@ -362,6 +362,9 @@ __global__ void bg_bisto_final_kernel(void* ws, BgLayout L, int src) {
 // ---------------------------------------------------------------------------------------------
 // 5. solver
 // ---------------------------------------------------------------------------------------------
+#ifndef IRB_BG_RECORDS
+#define IRB_BG_RECORDS 1
+#endif
 struct SolveArgs {
     const float* pred;   // [B,ch,P]  (forward: target; backward: target for grad_conf)
     const float* conf;   // [B,1,P]
@@ -431,10 +434,17 @@ __global__ void bg_setup_kernel(void* ws, BgLayout L, SolveArgs a) {
         at<double>(ws, L.wsplat)[(size_t)b * P + t] = wsum;
         at<double>(ws, L.minv)[(size_t)b * P + t] = 1.0 / fmax(diag, a.dmin);
         const double den = a.adjoint ? at<double>(ws, L.m0)[(size_t)b * P + t] : fmax(wsum, 1e-10);
+        double x0[BG_MAX_CH] = {0, 0, 0, 0};
         for (int c = 0; c < L.ch; ++c) {
             at<double>(ws, L.bvec)[((size_t)b * L.ch + c) * P + t] = bsum[c];
-            a.x[((size_t)b * L.ch + c) * P + t] = bsum[c] / den;
+            x0[c] = bsum[c] / den;
+            a.x[((size_t)b * L.ch + c) * P + t] = x0[c];
         }
+#if IRB_BG_RECORDS
+        // vertex-major record {x0_0..x0_2, n} for bg_r0_rec_kernel's neighbour gathers (same slot the PCG records use later)
+        if (L.ch == 1) at<double2>(ws, L.np)[(size_t)b * P + t] = make_double2(x0[0], n);
+        else if (L.ch <= 3) at<double4>(ws, L.np)[(size_t)b * P + t] = make_double4(x0[0], x0[1], x0[2], n);
+#endif
     }
     for (int c = 0; c < L.ch; ++c) block_atomic_add(ok ? bsum[c] * bsum[c] : 0.0, scal_ptr(ws, L, b, c, BG_MAX_ITERS + 1));
 }
@@ -643,9 +653,6 @@ __global__ void __launch_bounds__(256, IRB_BG_MINB) bg_xr_kernel(void* ws, BgLay
 // contracted), so the arithmetic of the solve is unchanged (results still vary in the last bits with the order of the fp64
 // atomics of the dot products, as before) -- and the own p and n come out of the same load.  Doubles moved per vertex
 // and iteration: 3 channels 52 -> 46, 1 channel 30 -> 24; a one-channel gather fetches 16 instead of 32 bytes.
-#ifndef IRB_BG_RECORDS
-#define IRB_BG_RECORDS 1
-#endif
 template <int CH> struct BgRec { typedef double4 T; };
 template <> struct BgRec<1> { typedef double2 T; };
 template <int CH> __device__ __forceinline__ void rec_unpack(const typename BgRec<CH>::T& r, double (&p)[3], double& n);
@@ -686,6 +693,42 @@ __global__ void __launch_bounds__(256, IRB_BG_MINB) bg_p_rec_kernel(void* ws, Bg
     *rec = rec_pack<CH>(pn, nv);
 }
 
+// blur part of A y for the vertex t from the records: bl[c] = 2 dim n_t y_t[c] + sum_dims (n_lo y_lo[c] + n_hi y_hi[c]), the
+// summation order of bg_blur; also returns the vertex's own y and n
+template <int CH>
+__device__ __forceinline__ void rec_blur(const typename BgRec<CH>::T* __restrict__ rec, const int* __restrict__ nbr, size_t P,
+                                         size_t t, double (&bl)[3], double (&yv)[3], double& nv) {
+    rec_unpack<CH>(rec[t], yv, nv);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) bl[c] = 0.0;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) bl[c] = 2.0 * BG_DIM * __dmul_rn(nv, yv[c]);
+#pragma unroll
+    for (int d = 0; d < BG_DIM; ++d) {
+        const int lo = ld_stream(nbr + (size_t)(2 * d) * P + t), hi = ld_stream(nbr + (size_t)(2 * d + 1) * P + t);
+        double tt[3] = {0.0, 0.0, 0.0};
+        bool any = false;
+        if (lo >= 0) {
+            double pj[3], nj;
+            rec_unpack<CH>(rec[lo], pj, nj);
+#pragma unroll
+            for (int c = 0; c < CH; ++c) tt[c] = __dmul_rn(nj, pj[c]);   // rounded product, never contracted into the add below
+            any = true;
+        }
+        if (hi >= 0) {
+            double pj[3], nj;
+            rec_unpack<CH>(rec[hi], pj, nj);
+#pragma unroll
+            for (int c = 0; c < CH; ++c) tt[c] = any ? tt[c] + __dmul_rn(nj, pj[c]) : __dmul_rn(nj, pj[c]);
+            any = true;
+        }
+        if (any) {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) bl[c] += tt[c];
+        }
+    }
+}
+
 template <int CH>
 __global__ void __launch_bounds__(256, IRB_BG_MINB) bg_q_rec_kernel(void* ws, BgLayout L, SolveArgs a, int it) {
     typedef typename BgRec<CH>::T Rec;
@@ -697,35 +740,7 @@ __global__ void __launch_bounds__(256, IRB_BG_MINB) bg_q_rec_kernel(void* ws, Bg
     double bl[3] = {0.0, 0.0, 0.0}, pv[3] = {0.0, 0.0, 0.0};
     double nv = 0.0, mv = 0.0, wsp = 0.0;
     if (ok) {
-        const Rec* rec = at<Rec>(ws, L.np) + (size_t)b * P;
-        const int* nbr = at<int>(ws, L.nbr) + (size_t)b * 2 * BG_DIM * P;
-        rec_unpack<CH>(rec[t], pv, nv);
-#pragma unroll
-        for (int c = 0; c < CH; ++c) bl[c] = 2.0 * BG_DIM * __dmul_rn(nv, pv[c]);
-#pragma unroll
-        for (int d = 0; d < BG_DIM; ++d) {   // same summation order as bg_blur: per dimension (lo + hi), then accumulate
-            const int lo = ld_stream(nbr + (size_t)(2 * d) * P + t), hi = ld_stream(nbr + (size_t)(2 * d + 1) * P + t);
-            double tt[3] = {0.0, 0.0, 0.0};
-            bool any = false;
-            if (lo >= 0) {
-                double pj[3], nj;
-                rec_unpack<CH>(rec[lo], pj, nj);
-#pragma unroll
-                for (int c = 0; c < CH; ++c) tt[c] = __dmul_rn(nj, pj[c]);   // rounded product, never contracted into the add below
-                any = true;
-            }
-            if (hi >= 0) {
-                double pj[3], nj;
-                rec_unpack<CH>(rec[hi], pj, nj);
-#pragma unroll
-                for (int c = 0; c < CH; ++c) tt[c] = any ? tt[c] + __dmul_rn(nj, pj[c]) : __dmul_rn(nj, pj[c]);
-                any = true;
-            }
-            if (any) {
-#pragma unroll
-                for (int c = 0; c < CH; ++c) bl[c] += tt[c];
-            }
-        }
+        rec_blur<CH>(at<Rec>(ws, L.np) + (size_t)b * P, at<int>(ws, L.nbr) + (size_t)b * 2 * BG_DIM * P, P, t, bl, pv, nv);
         mv = ld_stream(at<double>(ws, L.m) + (size_t)b * P + t);
         wsp = ld_stream(at<double>(ws, L.wsplat) + (size_t)b * P + t);
     }
@@ -742,6 +757,43 @@ __global__ void __launch_bounds__(256, IRB_BG_MINB) bg_q_rec_kernel(void* ws, Bg
         }
     }
     block_atomic_add_n<BG_MAX_CH>(pq, dst);
+}
+
+// r0 = b - A x0 ; rho0 = <r0, M r0> ; rr0 = <r0, r0>, x0 read from the records bg_setup wrote (one 32 / 16-byte gather per
+// neighbour for all channels; the legacy bg_r0_kernel gathers n and x separately, per channel: 60 gathers per vertex)
+template <int CH>
+__global__ void __launch_bounds__(256, IRB_BG_MINB) bg_r0_rec_kernel(void* ws, BgLayout L, SolveArgs a) {
+    typedef typename BgRec<CH>::T Rec;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y + a.b0;
+    const size_t P = L.P;
+    const int V = at<int>(ws, L.hdr)[b];
+    const bool ok = t < (size_t)V;
+    double sums[2 * CH];
+    double* dst[2 * CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        sums[2 * c] = sums[2 * c + 1] = 0.0;
+        dst[2 * c] = scal_ptr(ws, L, b, c, 0) + 0;
+        dst[2 * c + 1] = scal_ptr(ws, L, b, c, 0) + 2;
+    }
+    if (ok) {
+        double bl[3], xv[3], nv;
+        rec_blur<CH>(at<Rec>(ws, L.np) + (size_t)b * P, at<int>(ws, L.nbr) + (size_t)b * 2 * BG_DIM * P, P, t, bl, xv, nv);
+        const double mv = ld_stream(at<double>(ws, L.m) + (size_t)b * P + t);
+        const double wsp = ld_stream(at<double>(ws, L.wsplat) + (size_t)b * P + t);
+        const double mi = ld_stream(at<double>(ws, L.minv) + (size_t)b * P + t);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const size_t o = ((size_t)b * CH + c) * P + t;
+            const double Ax = a.lam * (mv * xv[c] - nv * bl[c]) + wsp * xv[c];
+            const double r = ld_stream(at<double>(ws, L.bvec) + o) - Ax;
+            st_stream(at<double>(ws, L.r) + o, r);
+            sums[2 * c] = r * mi * r;
+            sums[2 * c + 1] = r * r;
+        }
+    }
+    block_atomic_add_n<2 * CH>(sums, dst);
 }
 
 template <int CH>
@@ -834,6 +886,12 @@ static int run_pcg(void* ws, const BgLayout& L, SolveArgs a, int maxiter, cudaSt
         const dim3 grid(gx, (unsigned)(L.B - b0 < G ? L.B - b0 : G));
         a.b0 = b0;
         bg_setup_kernel<<<grid, 256, 0, st>>>(ws, L, a);
+#if IRB_BG_RECORDS
+        if (L.ch == 1) bg_r0_rec_kernel<1><<<grid, 256, 0, st>>>(ws, L, a);
+        else if (L.ch == 2) bg_r0_rec_kernel<2><<<grid, 256, 0, st>>>(ws, L, a);
+        else if (L.ch == 3) bg_r0_rec_kernel<3><<<grid, 256, 0, st>>>(ws, L, a);
+        else
+#endif
         bg_r0_kernel<<<grid, 256, 0, st>>>(ws, L, a);
         for (int it = 0; it < maxiter; ++it) {
 #if IRB_BG_RECORDS
