@@ -12,6 +12,12 @@
 #ifndef IRB_SGENV_FWD_MINB
 #define IRB_SGENV_FWD_MINB 4
 #endif
+#ifndef IRB_SGENV_BWD_MINB
+#define IRB_SGENV_BWD_MINB 3
+#endif
+#ifndef IRB_SGENV_RECONST_MINB
+#define IRB_SGENV_RECONST_MINB 2   // loss + gradient sweep: 250 registers, no spills; 573 -> 535 us (profiles/r02/ab_occupancy.txt)
+#endif
 
 namespace irb {
 
@@ -65,7 +71,7 @@ __device__ __forceinline__ float fast_log(float x) {   // natural log via lg2.ap
 }
 
 template <int MODE, int TPP>
-__global__ void __launch_bounds__(128, ((MODE == 1 || MODE >= 4) ? 3 : IRB_SGENV_FWD_MINB)) sg_env_group_kernel(const SgEnvArgs s, const __grid_constant__ EnvTab tab,
+__global__ void __launch_bounds__(128, (MODE == 1 ? IRB_SGENV_BWD_MINB : (MODE >= 4 ? IRB_SGENV_RECONST_MINB : IRB_SGENV_FWD_MINB))) sg_env_group_kernel(const SgEnvArgs s, const __grid_constant__ EnvTab tab,
                                                               const __grid_constant__ TileMaps maps,
                                                               const unsigned total_tiles, const unsigned tiles_per_img) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
