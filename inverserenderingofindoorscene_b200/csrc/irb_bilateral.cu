@@ -299,18 +299,37 @@ __global__ void bg_nbr_kernel(void* ws, BgLayout L) {
     const unsigned long long* uk = at<unsigned long long>(ws, L.ukeys) + (size_t)b * P;
     int* nbr = at<int>(ws, L.nbr) + (size_t)b * 2 * BG_DIM * P;
     const long long key = (long long)uk[t];
-    long long hv = 1;
-    for (int d = 0; d < BG_DIM; ++d) {
-        for (int s = 0; s < 2; ++s) {
-            const long long target = key + (s ? hv : -hv);
-            int lo = 0, hi = V;  // lower bound
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if ((long long)uk[mid] < target) lo = mid + 1; else hi = mid;
-            }
-            nbr[(size_t)(2 * d + s) * P + t] = (lo < V && (long long)uk[lo] == target) ? lo : -1;
+    // ten lower-bound searches (hash +- 255^d) advanced in lock-step with the branch-free uniform binary search: every step
+    // issues ten independent loads instead of one (the one-search-at-a-time loop was a chain of ~180 dependent L2 loads per
+    // vertex: 182 us per build at config 4)
+    long long target[2 * BG_DIM];
+    int base[2 * BG_DIM];
+    {
+        long long hv = 1;
+#pragma unroll
+        for (int d = 0; d < BG_DIM; ++d) {
+            target[2 * d] = key - hv;
+            target[2 * d + 1] = key + hv;
+            base[2 * d] = base[2 * d + 1] = 0;
+            hv *= 255;
         }
-        hv *= 255;
+    }
+    for (int n = V; n > 1;) {
+        const int half = n >> 1;
+#pragma unroll
+        for (int j = 0; j < 2 * BG_DIM; ++j) base[j] = ((long long)uk[base[j] + half - 1] < target[j]) ? base[j] + half : base[j];
+        n -= half;
+    }
+#pragma unroll
+    for (int j = 0; j < 2 * BG_DIM; ++j) {
+        const long long k0 = (long long)uk[base[j]];
+        int lo = base[j];                                      // the lower bound is base or base + 1
+        bool hit = k0 == target[j];
+        if (k0 < target[j]) {
+            lo = base[j] + 1;
+            hit = lo < V && (long long)uk[lo] == target[j];
+        }
+        nbr[(size_t)j * P + t] = hit ? lo : -1;
     }
     // pixel counts m0 = S 1
     const int* vs = at<int>(ws, L.vstart) + (size_t)b * (P + 1);
