@@ -155,6 +155,42 @@ static int launch_sg_env_tile_fwd(const SgEnvArgs& s, const EnvTab& tab, cudaStr
     return check_launch(what);
 }
 
+// thread-per-pixel reconstruction statistics (MODE 2) / loss (MODE 3) with the ground truth staged by TMA; -100 = not taken
+template <int KC, int MODE>
+static int launch_sg_env_tile_stat(const SgEnvArgs& s, const EnvTab& tab, cudaStream_t st, const char* what) {
+    const size_t plane = (size_t)s.R * s.C;
+    constexpr unsigned DC = 8, S = 3;
+    if (tab.D % DC != 0 || plane >= 0x7fffffffull || env_tiles_disabled() || ((uintptr_t)s.env_gt & 15u)) return -100;
+    CUtensorMap gmap;
+    memset(&gmap, 0, sizeof(gmap));
+    if (!cached_env_tile_map(&gmap, s.env_gt, plane, (unsigned)tab.D, (size_t)s.B * 3, DC)) return -100;
+    const size_t tiles_per_img = (plane + RE_PT - 1) / RE_PT;
+    const size_t total = tiles_per_img * (size_t)s.B;
+    if (total >= 0x7fffffffull) return -100;
+    const size_t smem = (size_t)S * 3 * RE_PT * DC * 4 + S * (sizeof(uint64_t) + sizeof(unsigned));
+    int per_sm = 1;
+    if (int e = persistent_ctas_per_sm(sg_env_tile_stat_kernel<KC, MODE>, RE_PT, smem, &per_sm)) {
+        set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", what, smem, cudaGetErrorString((cudaError_t)e));
+        return e;
+    }
+    size_t grid = (size_t)cached_sms() * per_sm;
+    if (grid > total) grid = total;
+    if (const char* cap = getenv("IRB_TMA_MAX_CTAS")) {
+        const long c = atol(cap);
+        if (c > 0 && (size_t)c < grid) grid = (size_t)c;
+    }
+    sg_env_tile_stat_kernel<KC, MODE><<<(unsigned)grid, RE_PT, smem, st>>>(s, tab, gmap, (unsigned)total, (unsigned)tiles_per_img);
+    return check_launch(what);
+}
+template <int MODE>
+static int try_sg_env_tile_stat(const SgEnvArgs& s, const EnvTab& tab, cudaStream_t st, const char* what) {
+    const char* v = getenv("IRB_SGENV_VARIANT");
+    if (v && (v[0] == 'p' || v[0] == 'g')) return -100;
+    if (s.K == 12) return launch_sg_env_tile_stat<12, MODE>(s, tab, st, what);
+    if (s.K == 6) return launch_sg_env_tile_stat<6, MODE>(s, tab, st, what);
+    return -100;
+}
+
 static int mk_tab(EnvTab& tab, int envH, int envW, int B, const char* who) {
     if (!make_env_tab(tab, envH, envW)) {
         set_error("%s: env table %dx%d unsupported (need envH*envW <= %d, multiple of 4)", who, envH, envW, IRB_MAX_DIRS);
@@ -251,7 +287,18 @@ extern "C" int irb_sg_reconst_fwd(const float* axis, const float* lamb, const fl
         set_error("sg_reconst_fwd: memset: %s", cudaGetErrorString(e));
         return (int)e;
     }
-    int rc;
+    int rc = try_sg_env_tile_stat<2>(s, tab, st, "sg_reconst_fwd(stats,tile)");
+    if (rc != -100) {   // statistics done by the tile kernel; second pass
+        if (rc) return rc;
+        if (!with_grads) {
+            rc = try_sg_env_tile_stat<3>(s, tab, st, "sg_reconst_fwd(loss,tile)");
+            if (rc != -100) return rc;
+        }
+        if (K <= 6) return with_grads ? launch_sg_group(sg_env_group_kernel<5, 1>, s, tab, 128, st, "sg_reconst_fwd(loss+grad)")
+                                      : launch_sg_group(sg_env_group_kernel<3, 1>, s, tab, 128, st, "sg_reconst_fwd(loss)");
+        return with_grads ? launch_sg_group(sg_env_group_kernel<5, 2>, s, tab, 64, st, "sg_reconst_fwd(loss+grad)")
+                          : launch_sg_group(sg_env_group_kernel<3, 2>, s, tab, 64, st, "sg_reconst_fwd(loss)");
+    }
     if (K <= 6) {
         rc = launch_sg_group(sg_env_group_kernel<2, 1>, s, tab, 128, st, "sg_reconst_fwd(stats)");
         if (!rc) rc = with_grads ? launch_sg_group(sg_env_group_kernel<5, 1>, s, tab, 128, st, "sg_reconst_fwd(loss+grad)")

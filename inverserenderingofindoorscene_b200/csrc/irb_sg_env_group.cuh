@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(128, (MODE == 1 ? IRB_SGENV_BWD_MINB : (MODE >
                             const float ce = coef4 * Ecd + s.offset;
                             const float dl = fast_log(ce) - fast_log(G[c][u] + s.offset);
                             if (MODE == 5) lacc = fmaf(dl, dl, lacc);
-                            G[c][u] = gfac * dl * x_rcp(ce);
+                            G[c][u] = (sg4 != 0.f) ? gfac * dl * x_rcp(ce) : 0.f;   // masked-out pixel: its ground truth is never looked at
                         }
                     }
                     const pk2 G0 = pk(G[0][u], G[0][u]), G1 = pk(G[1][u], G[1][u]), G2 = pk(G[2][u], G[2][u]);
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(128, (MODE == 1 ? IRB_SGENV_BWD_MINB : (MODE >
                 }
             }
             // every lane of a group holds the same sum; lanes past the end of the plane worked on unstaged data
-            if (MODE == 5) sg_block_add((active && h == 0) ? lacc * sg4 : 0.f, s.stats + b * 4 + 2);
+            if (MODE == 5) sg_block_add((active && h == 0 && sg4 != 0.f) ? lacc * sg4 : 0.f, s.stats + b * 4 + 2);
             if (active) {
 #pragma unroll
                 for (int i = 0; i < NP2; ++i) {

@@ -151,4 +151,151 @@ __global__ void __launch_bounds__(RE_PT, IRB_SGT_MINB)
     tma_store_wait_all();   // threads that never stored return at once
 }
 
+// ---- reconstruction statistics / loss against a ground-truth env-map, thread per pixel ----------------------------------
+// MODE 2: per-image regression sums  sum(E G s^2), sum(E^2 s^2), sum(s)     (models.LSregress, models.py:7-21)
+// MODE 3: numerator  sum((log(c E + off) - log(G + off))^2 s)               (wrapperBRDFLight.py:183-187)
+// Same arithmetic per (pixel, direction, channel) as sg_env_group_kernel<2|3,TPP>; here the predicted radiance E is formed
+// like in sg_env_tile_fwd_kernel (all K lobes in one thread) and the ground truth arrives through a 3-stage TMA ring of
+// [3 ch][128 px][8 dir] tiles (coalesced; the group kernel reads 16 bytes per lane at a 512-byte stride).
+#ifndef IRB_SGT_STAT_MINB
+#define IRB_SGT_STAT_MINB 4
+#endif
+template <int KC, int MODE>
+__global__ void __launch_bounds__(RE_PT, IRB_SGT_STAT_MINB)
+    sg_env_tile_stat_kernel(const SgEnvArgs s, const __grid_constant__ EnvTab tab, const __grid_constant__ CUtensorMap gmap,
+                            const unsigned total_tiles, const unsigned tiles_per_img) {
+    constexpr int DC = 8, CH_BYTES = RE_PT * DC * 4, STAGE_BYTES = 3 * CH_BYTES, S = 3, NP2 = KC / 2, NWARP = RE_PT / 32;
+    extern __shared__ __align__(1024) unsigned char sgs_smem[];
+    uint64_t* const full_bar = reinterpret_cast<uint64_t*>(sgs_smem + S * STAGE_BYTES);
+    unsigned* const done_cnt = reinterpret_cast<unsigned*>(full_bar + S);
+    if (threadIdx.x == 0) {
+        if (smem_u32(sgs_smem) & 1023u) __trap();
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+            mbar_init(&full_bar[i], 1);
+            done_cnt[i] = 0u;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const size_t plane = (size_t)s.R * s.C;
+    const int D = tab.D, nchunk = D / DC;
+    const int row = threadIdx.x;
+    const unsigned my_tiles = blockIdx.x < total_tiles ? (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+    const unsigned G = my_tiles * (unsigned)nchunk;
+    auto issue = [&](unsigned g) {   // fill stage g % S with chunk g of the ground truth
+        const unsigned t = blockIdx.x + (g / (unsigned)nchunk) * gridDim.x;
+        const int d0 = (int)(g % (unsigned)nchunk) * DC, b = (int)(t / tiles_per_img), pix0 = (int)(t % tiles_per_img) * RE_PT;
+        unsigned char* st = sgs_smem + (size_t)(g % S) * STAGE_BYTES;
+        uint64_t* bar = &full_bar[g % S];
+        mbar_expect_tx(bar, (uint32_t)STAGE_BYTES);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tma_load_3d(st + c * CH_BYTES, &gmap, d0, pix0, b * 3 + c, bar);
+    };
+    if (threadIdx.x == 0)
+        for (unsigned g = 0; g < (unsigned)S && g < G; ++g) issue(g);
+    unsigned g = 0;
+    for (unsigned tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int b = (int)(tile / tiles_per_img), pix0 = (int)(tile % tiles_per_img) * RE_PT;
+        const bool active = (size_t)pix0 + row < plane;
+        const size_t pix = active ? (size_t)pix0 + row : (size_t)pix0;
+        LobesPk<KC> Lp;
+        pk2 W2[3][NP2];
+        {
+            float ax[KC][3], lm[KC], W[KC][3];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const size_t oa = (((size_t)b * KC + k) * 3) * plane + pix;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    ax[k][c] = __ldg(s.axis + oa + c * plane);
+                    W[k][c] = __ldg(s.weight + ((size_t)b * (3 * KC) + 3 * k + c) * plane + pix);
+                }
+                lm[k] = __ldg(s.lamb + ((size_t)b * KC + k) * plane + pix);
+            }
+            Lobes<float, KC> L;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {   // same arithmetic as load_lobes / load_weight (irb_driver.cuh)
+                float lam = lm[k];
+                if (s.warp) lam = sg_warp<float>(lam);
+                lam *= Consts<float>::LOG2E;
+                L.lam[k] = lam;
+                L.bx[k] = lam * ax[k][0];
+                L.by[k] = lam * ax[k][1];
+                L.bz[k] = lam * ax[k][2];
+                if (s.warp) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) W[k][c] = sg_warp<float>(W[k][c]);
+                }
+            }
+            pack_lobes<KC>(Lp, L);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int i = 0; i < NP2; ++i) W2[c][i] = pk(W[2 * i][c], W[2 * i + 1][c]);
+        }
+        const float sg = active ? s.seg[(size_t)b * plane + pix] : 0.f;
+        const float coef = (MODE == 3) ? reconst_coef(s.stats + (size_t)b * 4) : 1.f;
+        float acc0 = 0.f, acc1 = 0.f;
+        for (int d0 = 0; d0 < D; d0 += DC, ++g) {
+            const int stage = (int)(g % S);
+            mbar_wait(&full_bar[stage], (g / S) & 1);
+            const unsigned char* st = sgs_smem + (size_t)stage * STAGE_BYTES;
+#pragma unroll
+            for (int j = 0; j < DC / 4; ++j) {
+                const int off = re_off<DC>(row, j);
+                float4 gq[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) gq[c] = *reinterpret_cast<const float4*>(st + c * CH_BYTES + off);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int d = d0 + 4 * j + u;
+                    const float wx = tab.lx[d], wy = tab.ly[d], wz = tab.lz[d];
+                    pk2 arg[NP2], e[NP2];
+                    lobe_exps_pk<KC>(Lp, pk(wx, wx), pk(wy, wy), pk(wz, wz), arg, e);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        pk2 acc = mul2(W2[c][0], e[0]);
+#pragma unroll
+                        for (int i = 1; i < NP2; ++i) acc = fma2(W2[c][i], e[i], acc);
+                        const float E = hsum2(acc);
+                        const float Gv = u == 0 ? gq[c].x : (u == 1 ? gq[c].y : (u == 2 ? gq[c].z : gq[c].w));
+                        if (MODE == 2) {
+                            acc0 = fmaf(E, Gv, acc0);
+                            acc1 = fmaf(E, E, acc1);
+                        } else {
+                            const float dl = fast_log(coef * E + s.offset) - fast_log(Gv + s.offset);
+                            acc0 = fmaf(dl, dl, acc0);
+                        }
+                    }
+                }
+            }
+            // the warp that is through with the stage last refills it with chunk g + S (irb_render_env_tma.cuh)
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) {
+                unsigned old;
+                asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(&done_cnt[stage])) : "memory");
+                if (old == (unsigned)(NWARP - 1)) {
+                    done_cnt[stage] = 0u;
+                    if (g + S < G) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        issue(g + S);
+                    }
+                }
+            }
+        }
+        // per-pixel weights as in the group kernel: the regression sees (E s)(G s) and (E s)^2, the loss dlog^2 * s;
+        // pixels outside the mask contribute exactly zero there too (s = 0)
+        double* stt = s.stats + (size_t)b * 4;
+        const bool in = sg != 0.f;   // like the group kernel: a masked-out pixel's values are never looked at (NaN-safe)
+        if (MODE == 2) {
+            sg_block_add(in ? acc0 * sg * sg : 0.f, stt + 0);
+            sg_block_add(in ? acc1 * sg * sg : 0.f, stt + 1);
+            sg_block_add(sg, stt + 3);
+        } else {
+            sg_block_add(in ? acc0 * sg : 0.f, stt + 2);
+        }
+    }
+}
+
 }  // namespace irb

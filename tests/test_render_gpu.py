@@ -641,3 +641,42 @@ def test_sg_to_env_tile_ring(irb, K, cap, monkeypatch):
             e64 = store[0]
         else:
             check_parity(tile[0].cpu().numpy(), e64, store[0], 'env')
+
+
+@pytest.mark.parametrize('K', [12, 6])
+def test_reconst_tile_stats_ring(irb, K, monkeypatch):
+    """reconstruction statistics / loss passes as thread-per-pixel tile kernels (ground truth through a 3-stage TMA ring,
+    grid capped to 2 CTAs, last tile partial, masked-out pixels holding NaN in the ground truth): same numbers as the
+    lobe-split kernels, with and without gradients, and the gradients of the SG heads agree"""
+    from oracle import render_oracle as ro
+    B, R, C = 2, 17, 28          # plane = 476 = 3 full tiles + 92 px
+    ins64 = ro.synth_inputs(B, R, C, R, C, K, seed=5 + K, dtype=torch.float64, hi=0.9)
+    dev = torch.device('cuda')
+    g = torch.Generator().manual_seed(9)
+    env_gt = (torch.rand(B, 3, R, C, 8, 16, generator=g) * 2).to(dev)
+    seg = (torch.rand(B, 1, R, C, generator=g) > 0.25).float().to(dev)
+    env_gt = torch.where(seg.view(B, 1, R, C, 1, 1) > 0, env_gt, torch.full_like(env_gt, float('nan')))
+    o2e = irb.output2env(K, isCuda=True)
+
+    def run(grads):
+        heads = [t.float().to(dev).requires_grad_(grads) for t in ins64[3:]]
+        if grads:
+            err, coef = o2e.reconstLoss(heads[0], heads[1], heads[2], env_gt, seg)
+            gg = torch.autograd.grad(err, heads)
+        else:
+            with torch.no_grad():
+                err, coef = o2e.reconstLoss(heads[0], heads[1], heads[2], env_gt, seg)
+            gg = []
+        torch.cuda.synchronize()
+        return [err.detach(), coef.detach()] + [x.detach() for x in gg]
+    monkeypatch.setenv('IRB_SGENV_VARIANT', 'group')
+    ref_g, ref_n = run(True), run(False)
+    monkeypatch.delenv('IRB_SGENV_VARIANT')
+    monkeypatch.setenv('IRB_TMA_MAX_CTAS', '2')
+    til_g, til_n = run(True), run(False)
+    monkeypatch.delenv('IRB_TMA_MAX_CTAS')
+    names = ['err', 'coef', 'g_axis', 'g_lamb', 'g_weight', 'err(no grad)', 'coef(no grad)']
+    for a, b, n in zip(ref_g + ref_n, til_g + til_n, names):
+        assert torch.isfinite(a).all() and torch.isfinite(b).all(), n
+        e = relerr(b.cpu().numpy(), a.cpu().numpy())
+        assert e <= 5e-6, (n, e)
