@@ -242,13 +242,16 @@ __global__ void __launch_bounds__(128, (MODE == 1 ? IRB_SGENV_BWD_MINB : (MODE >
                         gW2[2][i] = fma2(G2, e[i], gW2[2][i]);
                         const pk2 tt = mul2(e[i], fma2(G0, W2[0][i], fma2(G1, W2[1][i], mul2(G2, W2[2][i]))));
                         S2[i] = fma2(tt, arg[i], S2[i]);
-                        N2[i] = add2(N2[i], tt);
                         mx2[i] = fma2(tt, wx2, mx2[i]);
                         my2[i] = fma2(tt, wy2, my2[i]);
                         mz2[i] = fma2(tt, wz2, mz2[i]);
                     }
                 }
             }
+            // N_k = sum_d tt_kd = sum_c W_kc gW_kc (gW_kc = sum_d G_cd e_kd): formed once here instead of one packed add per
+            // lobe pair and direction (1 of the loop's 15 FMA-pipe instructions)
+#pragma unroll
+            for (int i = 0; i < NP2; ++i) N2[i] = fma2(W2[0][i], gW2[0][i], fma2(W2[1][i], gW2[1][i], mul2(W2[2][i], gW2[2][i])));
             // every lane of a group holds the same sum; lanes past the end of the plane worked on unstaged data
             if (MODE == 5) sg_block_add((active && h == 0 && sg4 != 0.f) ? lacc * sg4 : 0.f, s.stats + b * 4 + 2);
             if (active) {
