@@ -158,7 +158,9 @@ int irb_lsregress(const float* pred, const float* gt, const float* origin, float
  * fwd: when any of g_axis / g_lamb / g_weight is non-null the second pass also writes d(sum_b num_b)/d(parameter)
  * (unit upstream gradient; the caller scales these small tensors), so a training step needs two passes, not three.
  * bwd: g_num = device scalar dL/d(sum_b num_b); writes the gradients w.r.t. the ORIGINAL SG parameters (coef is a
- * graph constant as in models.py:13).  Needs K <= 24, R*C % 4 == 0, 16-byte aligned buffers (else IRB_E_UNSUPPORTED). */
+ * graph constant as in models.py:13).  Needs K <= 24, R*C % 4 == 0, 16-byte aligned buffers (else IRB_E_UNSUPPORTED).
+ * Pixels with seg == 0 contribute exactly zero and their env_gt values are never looked at (a NaN / Inf there stays out of
+ * the loss and of the gradients; the reference's `(...)**2 * seg` would propagate it). */
 int irb_sg_reconst_fwd(const float* axis, const float* lamb, const float* weight, const float* env_gt, const float* seg,
                        double* stats, float* g_axis, float* g_lamb, float* g_weight, int B, int K, int R, int C, int envH,
                        int envW, int warp, float offset, void* stream);
